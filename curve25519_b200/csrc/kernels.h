@@ -1,0 +1,34 @@
+// kernels.h -- internal launcher interface between the host-side C ABI (engine.cu) and the kernel
+// translation units.  Not installed; the public boundary is include/c25519_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace c25519 {
+
+// one 8-fold base-point table entry = (Y+X, Y-X, 2dT), 3 x 8 limbs (PA_POINT, curve25519_mehdi.h:77-82)
+constexpr int kCombEntries = 256;
+constexpr int kCombWordsPerEntry = 24;
+constexpr int kCombTableBytes = kCombEntries * kCombWordsPerEntry * 4;   // 24 576
+
+// device copy of the comb table (global memory; staged into shared memory per CTA by TMA bulk copy)
+extern const uint32_t* g_comb_table_dev;
+
+cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s);
+cudaError_t launch_x25519_comb(uint8_t* pk32, uint8_t* sk32_inout, size_t n, const uint32_t* table, cudaStream_t s);
+cudaError_t launch_ed25519_keypair(uint8_t* pub32, uint8_t* priv64, const uint8_t* seed32, size_t n, const uint32_t* table, cudaStream_t s);
+cudaError_t launch_ed25519_sign(uint8_t* sig64, const uint8_t* priv64, const uint8_t* msgs, const uint64_t* off, size_t fixed_len,
+                                size_t n, const uint32_t* table, cudaStream_t s);
+cudaError_t launch_ed25519_verify(int32_t* ok, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msgs, const uint64_t* off,
+                                  size_t fixed_len, size_t n, const uint32_t* table, cudaStream_t s);
+cudaError_t launch_ed25519_verify_init(uint8_t* ctx, const uint8_t* pk32, size_t n_keys, cudaStream_t s);
+cudaError_t launch_ed25519_verify_check(int32_t* ok, const uint8_t* ctx, const uint32_t* key_index, const uint8_t* sig64,
+                                        const uint8_t* msgs, const uint64_t* off, size_t fixed_len, size_t n,
+                                        const uint32_t* table, cudaStream_t s);
+cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s);
+cudaError_t launch_imad_peak(uint64_t* mac_per_launch, uint32_t* sink, int iters, cudaStream_t s);
+
+void count_launch();
+
+}  // namespace c25519

@@ -1,0 +1,84 @@
+// x25519.cuh -- Montgomery-ladder X25519 (variable base), one scalar multiplication per thread.
+//
+// Replaces source/curve25519_dh.c of the reference on the GPU:
+//   ecp_MontDouble :40-54 -> mont_double     ecp_Mont :57-84 -> mont_step     ecp_PointMultiply :94-157 -> x25519_ladder
+//
+// Same algorithm shape as the reference (start from the top set bit with P = (u:1), Q = 2P, then one
+// "P <- P+Q, Q <- 2Q" step per remaining bit with the roles of P and Q chosen by the bit), with the
+// reference's pointer-table operand selection (ECP_MONT :89) replaced by a lane-uniform conditional
+// register swap, and its projective-Z randomisation (:123) dropped (result-neutral).
+// All 256 bits of u are used (no bit-255 masking, :104); Z = 0 at the end gives 32 zero bytes (:148-150).
+#pragma once
+#include "fe25519.cuh"
+
+namespace c25519 {
+
+// (X2:Z2) = 2 (X:Z)                                   2S + 2M + 1W + 3A
+C25519_DEV void mont_double(fe& X2, fe& Z2, const fe& X, const fe& Z)
+{
+    fe A, B;
+    fe_add(A, X, Z);
+    fe_sub(B, X, Z);
+    fe_sqr(A, A);
+    fe_sqr(B, B);
+    fe_mul(X2, A, B);
+    fe_sub(B, A, B);
+    fe_mul_small_add(A, A, 121665u, B);
+    fe_mul(Z2, A, B);
+}
+
+// (S,D) <- (S + D, 2 D) where S - D = (base : 1).      5M + 4S + 1W + 7A     -- the hot loop body
+// SX,SZ,DX,DZ are N (outputs of fe_mul/fe_sqr) on entry and on exit.
+C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
+{
+    fe A, B, C, D;
+    fe_sub(A, SX, SZ);
+    fe_add_nn(B, SX, SZ);
+    fe_sub(C, DX, DZ);
+    fe_add_nn(D, DX, DZ);
+    fe_mul(A, A, D);
+    fe_mul(B, B, C);
+    fe_add_nn(SX, A, B);
+    fe_sub(B, A, B);
+    fe_sqr(SX, SX);
+    fe_sqr(A, B);
+    fe_mul(SZ, A, base);
+    fe_sqr(A, D);
+    fe_sqr(B, C);
+    fe_mul(DX, A, B);
+    fe_sub(B, A, B);
+    fe_mul_small_add(A, A, 121665u, B);
+    fe_mul(DZ, A, B);
+}
+
+// out = canonical x-coordinate of [k]u.   k must have bit 254 set and bit 255 clear (clamped);
+// kw(w) returns 32-bit word w of k.
+template <typename KeyWord>
+C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)
+{
+    fe R0X, R0Z, R1X, R1Z;          // R0 = P, R1 = Q while `cur` is true
+    fe_copy(R0X, u);
+    fe_set_u32(R0Z, 1);
+    mont_double(R1X, R1Z, R0X, R0Z);
+    // make R0X narrow: u is an arbitrary 256-bit value, the step wants N inputs for its lazy additions
+    { fe one; fe_set_u32(one, 1); fe_mul(R0X, R0X, one); }
+    bool cur = true;
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; --bit) {
+        bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
+        bool s = (b != cur);
+        fe_cswap(R0X, R1X, s);
+        fe_cswap(R0Z, R1Z, s);
+        cur = b;
+        mont_step(R0X, R0Z, R1X, R1Z, u);    // bit = 1: P += Q, Q = 2Q ; bit = 0: Q += P, P = 2P
+    }
+    fe PX, PZ;
+    fe_select(PX, R1X, R0X, cur);
+    fe_select(PZ, R1Z, R0Z, cur);
+    fe zi;
+    fe_invert(zi, PZ);
+    fe_mul(out, PX, zi);
+    fe_canon(out);
+}
+
+}  // namespace c25519

@@ -1,0 +1,136 @@
+"""GPU parity for the X25519 path, through the C ABI (device-pointer and host-pointer flavours and the
+n = 1 legacy wrappers), against the CPU checkers, the RFC 7748 vectors and the committed golden fixtures.
+Bit-exact: outputs AND the in-place-clamped secret keys must match byte for byte."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import vectors as V
+from tests.conftest import hx
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rows(hexes):
+    return np.stack([hx(h) for h in hexes])
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_kat_vectors(engine):
+    sk = _rows([k for k, _, _, _ in V.X25519_KAT]); pk = _rows([u for _, u, _, _ in V.X25519_KAT])
+    out, skc = engine.x25519_shared(_dev(pk), _dev(sk))
+    out = out.cpu().numpy(); skc = skc.cpu().numpy()
+    for i, (_, _, exp, note) in enumerate(V.X25519_KAT):
+        assert out[i].tobytes().hex() == exp, note
+    exp_sk = sk.copy(); exp_sk[:, 0] &= 0xF8; exp_sk[:, 31] = (exp_sk[:, 31] | 0x40) & 0x7F
+    assert (skc == exp_sk).all()
+
+
+def test_low_order_points_give_zero(engine):
+    pk = _rows(V.X25519_LOW_ORDER_U)
+    sk = np.tile(hx(V.X25519_KAT[3][0]), (pk.shape[0], 1))
+    out, _ = engine.x25519_shared(_dev(pk), _dev(sk))
+    assert not out.cpu().numpy().any()
+
+
+def test_golden_fixture(engine):
+    g = json.load(open(os.path.join(GOLD, "x25519.json")))
+    sk = _rows(g["sk"]); pk = _rows(g["pk"])
+    out, skc = engine.x25519_shared(_dev(pk), _dev(sk))
+    assert [r.tobytes().hex() for r in out.cpu().numpy()] == g["shared"]
+    assert [r.tobytes().hex() for r in skc.cpu().numpy()] == g["sk_clamped"]
+    for ladder in (True, False):
+        pub, _ = engine.x25519_public(_dev(sk), ladder=ladder)
+        assert [r.tobytes().hex() for r in pub.cpu().numpy()] == g["public"], ladder
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 127, 128, 129, 1000, 20000])
+def test_random_batches_vs_oracle(engine, oracle, rng, n):
+    """Ragged batch sizes around warp / CTA boundaries; uniform random scalars and points, no pre-clamping,
+    no bit-255 masking."""
+    sk = rng.integers(0, 256, (n, 32), dtype=np.uint8); pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    exp, exp_sk = oracle.x25519_shared(pk, sk, threads=os.cpu_count() or 1)
+    out, skc = engine.x25519_shared(_dev(pk), _dev(sk))
+    assert (out.cpu().numpy() == exp).all() and (skc.cpu().numpy() == exp_sk).all()
+    # host-pointer flavour (H2D + kernel + D2H inside the call)
+    out_h, skc_h = engine.x25519_shared(pk, sk)
+    assert (out_h == exp).all() and (skc_h == exp_sk).all()
+
+
+def test_empty_batch(engine):
+    z = np.zeros((0, 32), np.uint8)
+    out, skc = engine.x25519_shared(z, z)
+    assert out.shape == (0, 32)
+    out, skc = engine.x25519_shared(_dev(z), _dev(z))
+    assert tuple(out.shape) == (0, 32)
+
+
+def test_public_ladder_vs_oracle(engine, oracle, rng):
+    sk = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    exp, exp_sk = oracle.x25519_public(sk, fast=True, threads=os.cpu_count() or 1)
+    for ladder in (True, False):
+        out, skc = engine.x25519_public(_dev(sk), ladder=ladder)
+        assert (out.cpu().numpy() == exp).all() and (skc.cpu().numpy() == exp_sk).all(), ladder
+    out, skc = engine.x25519_public(sk, ladder=False)
+    assert (out == exp).all() and (skc == exp_sk).all()
+
+
+def test_iterated_rfc7748(engine):
+    """RFC 7748 5.2 iterated test, 1 and 1000 iterations, through the n = 1 host path."""
+    k = hx("09" + "00" * 31)[None, :]; u = k.copy()
+    for i in range(1000):
+        out, _ = engine.x25519_shared(u, k)
+        u, k = k, out
+        if i == 0:
+            assert k[0].tobytes().hex() == V.X25519_ITER_1
+    assert k[0].tobytes().hex() == V.X25519_ITER_1000
+
+
+def test_legacy_wrappers(engine):
+    """The reference's own dh_test (test/curve25519_test.c:429-475) through the re-exported legacy symbols."""
+    from curve25519_b200 import _native
+    L = _native.lib()
+    a = (C.c_uint8 * 32).from_buffer_copy(bytes.fromhex(V.DH_TEST["alice_sk"]))
+    b = (C.c_uint8 * 32).from_buffer_copy(bytes.fromhex(V.DH_TEST["bruce_sk"]))
+    apk = (C.c_uint8 * 32)(); bpk = (C.c_uint8 * 32)(); s1 = (C.c_uint8 * 32)(); s2 = (C.c_uint8 * 32)()
+    L.curve25519_dh_CalculatePublicKey(apk, a)
+    L.curve25519_dh_CalculatePublicKey_fast(bpk, b)
+    assert bytes(apk).hex() == V.DH_TEST["alice_pk"] and bytes(bpk).hex() == V.DH_TEST["bruce_pk"]
+    assert (a[0] & 7) == 0 and (a[31] & 0xC0) == 0x40          # clamped in place
+    L.curve25519_dh_CreateSharedKey(s1, bpk, a)
+    L.curve25519_dh_CreateSharedKey(s2, apk, b)
+    assert bytes(s1).hex() == V.DH_TEST["shared"] == bytes(s2).hex()
+
+
+def test_full_size_1m_properties(engine, oracle, rng):
+    """BASELINE config 2 at full size (2^20 ops): size-independent properties plus a sampled oracle check.
+      * Diffie-Hellman commutativity: shared(a, pub(b)) == shared(b, pub(a)) for every pair
+      * 4096 randomly chosen records equal the oracle's output byte for byte
+      * clamping is idempotent and exactly the RFC mask"""
+    import torch
+    n = 1 << 20
+    sk_a = rng.integers(0, 256, (n, 32), dtype=np.uint8); sk_b = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    da, db = _dev(sk_a), _dev(sk_b)
+    pa, ca = engine.x25519_public(da, ladder=False); pb, cb = engine.x25519_public(db, ladder=False)
+    s1, ca2 = engine.x25519_shared(pb, da); s2, _ = engine.x25519_shared(pa, db)
+    assert torch.equal(s1, s2)
+    assert torch.equal(ca, ca2)
+    exp_sk = sk_a.copy(); exp_sk[:, 0] &= 0xF8; exp_sk[:, 31] = (exp_sk[:, 31] | 0x40) & 0x7F
+    assert (ca.cpu().numpy() == exp_sk).all()
+    idx = rng.choice(n, 4096, replace=False)
+    pb_h = pb.cpu().numpy()
+    exp, _ = oracle.x25519_shared(pb_h[idx], sk_a[idx], threads=os.cpu_count() or 1)
+    assert (s1.cpu().numpy()[idx] == exp).all()
+    # and uniformly random (mostly off-curve / twist, bit 255 set in half) peer points at full size, sampled
+    pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    s3, _ = engine.x25519_shared(_dev(pk), da)
+    exp, _ = oracle.x25519_shared(pk[idx], sk_a[idx], threads=os.cpu_count() or 1)
+    assert (s3.cpu().numpy()[idx] == exp).all()
