@@ -65,9 +65,15 @@ int ensure_init_locked()
     CK(cudaGetDeviceProperties(&p, dev));
     if (p.major != 10) return fail(C25519_E_NO_DEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
     CK(cudaSetDevice(dev));
+    // device image of the comb table: entries padded from 24 to kCombStrideWords (28) words so one TMA bulk
+    // copy drops it into shared memory in its bank-conflict-avoiding layout (see ge25519.cuh)
+    static uint32_t padded[kCombEntries * kCombStrideWordsHost];
+    for (int e = 0; e < kCombEntries; e++)
+        for (int w = 0; w < kCombStrideWordsHost; w++)
+            padded[e * kCombStrideWordsHost + w] = w < kCombWordsPerEntry ? kCombTableHost[e * kCombWordsPerEntry + w] : 0u;
     uint32_t* t = nullptr;
-    CK(cudaMalloc(&t, kCombTableBytes));
-    CK(cudaMemcpy(t, kCombTableHost, kCombTableBytes, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&t, sizeof padded));
+    CK(cudaMemcpy(t, padded, sizeof padded, cudaMemcpyHostToDevice));
     g_comb_table_dev = t;
     for (auto& st : g_stage) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
     g_device = dev;

@@ -11,6 +11,7 @@ namespace c25519 {
 constexpr int kCombEntries = 256;
 constexpr int kCombWordsPerEntry = 24;
 constexpr int kCombTableBytes = kCombEntries * kCombWordsPerEntry * 4;   // 24 576
+constexpr int kCombStrideWordsHost = 28;   // padded device/shared-memory stride (== kCombStrideWords in ge25519.cuh)
 
 // device copy of the comb table (global memory; staged into shared memory per CTA by TMA bulk copy)
 extern const uint32_t* g_comb_table_dev;

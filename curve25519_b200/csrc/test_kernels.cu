@@ -4,6 +4,8 @@
 // IMAD.WIDE roofline denominator on the very device it is timing.
 #include "kernels.h"
 #include "fe25519.cuh"
+#include "sc25519.cuh"
+#include "sha512.cuh"
 
 namespace c25519 {
 
@@ -30,11 +32,41 @@ k_test_fe(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, cons
     fe_store(out + 32 * i, z);
 }
 
+// op 8: (a || b) as a 512-bit little-endian integer mod L -> 32 bytes;  op 9: SHA-512(a || b) -> 64 bytes
+__global__ void __launch_bounds__(128)
+k_test_sc_sha(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+    fe_load(x, a + 32 * i); fe_load(y, b + 32 * i);
+    if (op == 8) {
+        u32 w[16], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { w[k] = x.v[k]; w[8 + k] = y.v[k]; }
+        sc_reduce512(r, w);
+        fe z;
+#pragma unroll
+        for (int k = 0; k < 8; k++) z.v[k] = r[k];
+        fe_store(out + 32 * i, z);
+    } else {
+        u64 pre[8], dg[8]; u32 w[16];
+        le_limbs_to_be64(pre, x.v); le_limbs_to_be64(pre + 4, y.v);
+        sha512_prefixed<8>(dg, pre, nullptr, 0);
+        sha512_digest_to_le_words(w, dg);
+        fe lo, hi;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { lo.v[k] = w[k]; hi.v[k] = w[8 + k]; }
+        fe_store(out + 64 * i, lo); fe_store(out + 64 * i + 32, hi);
+    }
+}
+
 cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    k_test_fe<<<grid, 128, 0, s>>>(op, out, a, b, n);
+    if (op == 8 || op == 9) k_test_sc_sha<<<grid, 128, 0, s>>>(op, out, a, b, n);
+    else k_test_fe<<<grid, 128, 0, s>>>(op, out, a, b, n);
     count_launch();
     return cudaGetLastError();
 }
