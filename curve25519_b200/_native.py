@@ -42,6 +42,7 @@ def lib():
         "c25519_test_primitive": ([i32, vp, vp, vp, sz, vp], i32),
         "c25519_imad_peak_kernel": ([C.POINTER(u64), vp, i32, vp], i32),
         # the reference's 11-function API (include/c25519_legacy.h)
+        "ecp_TrimSecretKey": ([vp], None),
         "curve25519_dh_CalculatePublicKey": ([vp, vp], None),
         "curve25519_dh_CalculatePublicKey_fast": ([vp, vp], None),
         "curve25519_dh_CreateSharedKey": ([vp, vp, vp], None),

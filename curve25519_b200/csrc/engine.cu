@@ -353,6 +353,9 @@ static void die_if(int rc, const char* fn)
     abort();
 }
 
+// RFC 7748 clamp on a caller's host buffer (curve25519_utils.c:28-32); the batch kernels clamp on the device
+void ecp_TrimSecretKey(unsigned char* sk) { sk[0] &= 0xf8; sk[31] = (unsigned char)((sk[31] | 0x40) & 0x7f); }
+
 void curve25519_dh_CalculatePublicKey(unsigned char* pk, unsigned char* sk)
 { die_if(c25519_x25519_public_host(pk, sk, 1, 1), "curve25519_dh_CalculatePublicKey"); }
 

@@ -25,6 +25,10 @@ extern "C" {
 #define ed25519_private_key_size  64
 #define ed25519_signature_size    64
 
+/* Host-side key clamp exported by the reference's library and used by its own test program
+ * (source/curve25519_utils.c:28-32, declared in source/curve25519_mehdi.h:96): two byte masks, no curve work. */
+void ecp_TrimSecretKey(unsigned char *sk);
+
 void curve25519_dh_CalculatePublicKey(unsigned char *pk, unsigned char *sk);
 void curve25519_dh_CalculatePublicKey_fast(unsigned char *pk, unsigned char *sk);
 void curve25519_dh_CreateSharedKey(unsigned char *shared, const unsigned char *pk, unsigned char *sk);

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared(header):
     src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:c25519|curve25519_dh|ed25519)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:c25519|curve25519_dh|ed25519|ecp)_\w+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
