@@ -13,6 +13,7 @@
 // size as the reference's EDP_SIGV_CTX) live in HBM, one contiguous record per key.
 #include "kernels.h"
 #include "ge25519.cuh"
+#include "normalize.cuh"
 #include "sc25519.cuh"
 #include "sha512.cuh"
 
@@ -66,8 +67,15 @@ C25519_DEV void store8(uint8_t* p, const u32 (&w)[8])
 C25519_DEV void clamp(u32 (&k)[8]) { k[0] &= 0xfffffff8u; k[7] = (k[7] | 0x40000000u) & 0x7fffffffu; }   // ecp_TrimSecretKey
 
 // ---- X25519 public key through the comb -----------------------------------------------------------
+C25519_DEV void store_xyz(uint8_t* rec, const ge_ext& S)
+{ fe_store(rec, S.x); fe_store(rec + 32, S.y); fe_store(rec + 64, S.z); }
+
+// DEFER (all comb kernels): stop at the projective result, write it to the scratch record, and let
+// k_normalize finish the batch with one shared inversion per 16 operations (normalize.cuh).
+template <bool DEFER>
 __global__ void __launch_bounds__(kThreads)
-k_x25519_comb(uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n, const u32* __restrict__ gtable)
+k_x25519_comb(uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n, const u32* __restrict__ gtable,
+              uint8_t* __restrict__ scratch)
 {
     C25519_COMB_SMEM;
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -83,10 +91,15 @@ k_x25519_comb(uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n, 
     fe num, den, u;
     fe_add_nn(num, S.z, S.y);
     fe_sub(den, S.z, S.y);
-    fe_invert(den, den);
-    fe_mul(u, num, den);
-    fe_canon(u);
-    fe_store(pk32 + 32 * i, u);
+    if (DEFER) {
+        fe_store(scratch + kScratchXZ * i, num);
+        fe_store(scratch + kScratchXZ * i + 32, den);
+    } else {
+        fe_invert(den, den);
+        fe_mul(u, num, den);
+        fe_canon(u);
+        fe_store(pk32 + 32 * i, u);
+    }
 }
 
 // a = clamp(SHA512(seed)[0..31]) as limbs; also returns the upper half of the digest (the "prefix" b)
@@ -101,9 +114,10 @@ C25519_DEV void expand_seed(u32 (&a)[8], u32 (&b)[8], const u32 (&seed)[8])
     clamp(a);
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(kThreads)
 k_ed25519_keypair(uint8_t* __restrict__ pub32, uint8_t* __restrict__ priv64, const uint8_t* __restrict__ seed32, size_t n,
-                  const u32* __restrict__ gtable)
+                  const u32* __restrict__ gtable, uint8_t* __restrict__ scratch)
 {
     C25519_COMB_SMEM;
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -113,10 +127,14 @@ k_ed25519_keypair(uint8_t* __restrict__ pub32, uint8_t* __restrict__ priv64, con
     expand_seed(a, b, seed);
     ge_ext S;
     ge_base_comb(S, a, s_table);
-    ge_encode(enc, S);
-    store8(pub32 + 32 * i, enc);
     store8(priv64 + 64 * i, seed);
-    store8(priv64 + 64 * i + 32, enc);
+    if (DEFER) {
+        store_xyz(scratch + kScratchXYZ * i, S);          // k_normalize writes pub32[i] and priv64[i][32..64)
+    } else {
+        ge_encode(enc, S);
+        store8(pub32 + 32 * i, enc);
+        store8(priv64 + 64 * i + 32, enc);
+    }
 }
 
 C25519_DEV void msg_span(const uint8_t*& m, u64& len, const uint8_t* msgs, const uint64_t* off, size_t fixed_len, size_t i)
@@ -125,32 +143,56 @@ C25519_DEV void msg_span(const uint8_t*& m, u64& len, const uint8_t* msgs, const
     else { m = msgs + i * fixed_len; len = fixed_len; }
 }
 
+// PHASE 0: whole signature in one kernel (private inversion; tiny batches)
+// PHASE 1: [a:b] = H(sk), r = H(b || m) mod L, R = r B projective -> scratch (X, Y, Z, -, a); r parked in sig[32..64)
+// PHASE 2: (after k_normalize wrote enc(R) to sig[0..32))  h = H(enc(R) || pk || m) mod L,  S = (h a + r) mod L
+constexpr int kSignScratch = 160;                     // X, Y, Z, prefix, a
+template <int PHASE>
 __global__ void __launch_bounds__(kThreads)
 k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, const uint8_t* __restrict__ msgs,
-               const uint64_t* __restrict__ off, size_t fixed_len, size_t n, const u32* __restrict__ gtable)
+               const uint64_t* __restrict__ off, size_t fixed_len, size_t n, const u32* __restrict__ gtable,
+               uint8_t* __restrict__ scratch)
 {
-    C25519_COMB_SMEM;
+    __shared__ __align__(128) u32 s_table[PHASE == 2 ? 4 : kCombSmemWords];
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (PHASE != 2) stage_comb_table(s_table, &s_bar, gtable);
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     const uint8_t* m; u64 mlen;
     msg_span(m, mlen, msgs, off, fixed_len, i);
-    u32 seed[8], pk[8], a[8], b[8], r[8], enc[8];
-    load8(seed, priv64 + 64 * i);
-    load8(pk, priv64 + 64 * i + 32);
-    expand_seed(a, b, seed);                                   // [a:b] = H(sk)              (:385-389)
-    {   // r = H(b || m) mod L                                                               (:392-397)
-        u64 pre[4], dg[8]; u32 w[16];
-        le_limbs_to_be64(pre, b);
-        sha512_prefixed<4>(dg, pre, m, mlen);
-        sha512_digest_to_le_words(w, dg);
-        sc_reduce512(r, w);
-    }
-    {   // R = r B                                                                           (:400-401)
-        ge_ext S;
+    u32 a[8], r[8], enc[8];
+    if (PHASE != 2) {
+        u32 seed[8], b[8];
+        load8(seed, priv64 + 64 * i);
+        expand_seed(a, b, seed);                                   // [a:b] = H(sk)              (:385-389)
+        {   // r = H(b || m) mod L                                                               (:392-397)
+            u64 pre[4], dg[8]; u32 w[16];
+            le_limbs_to_be64(pre, b);
+            sha512_prefixed<4>(dg, pre, m, mlen);
+            sha512_digest_to_le_words(w, dg);
+            sc_reduce512(r, w);
+        }
+        ge_ext S;                                                  // R = r B                    (:400-401)
         ge_base_comb(S, r, s_table);
+        if (PHASE == 1) {
+            uint8_t* rec = scratch + (size_t)kSignScratch * i;
+            store_xyz(rec, S);
+            store8(rec + 128, a);
+            store8(sig64 + 64 * i + 32, r);
+            return;
+        }
         ge_encode(enc, S);
+    } else {
+        const uint4* q = reinterpret_cast<const uint4*>(sig64 + 64 * i);     // plain loads: written by earlier launches
+        uint4 e0 = q[0], e1 = q[1], r0 = q[2], r1 = q[3];
+        enc[0] = e0.x; enc[1] = e0.y; enc[2] = e0.z; enc[3] = e0.w; enc[4] = e1.x; enc[5] = e1.y; enc[6] = e1.z; enc[7] = e1.w;
+        r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+        const uint4* qa = reinterpret_cast<const uint4*>(scratch + (size_t)kSignScratch * i + 128);
+        uint4 a0 = qa[0], a1 = qa[1];
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
     }
-    u32 h[8], s[8];
+    u32 pk[8], h[8], s[8];
+    load8(pk, priv64 + 64 * i + 32);
     {   // h = H(enc(R) || pk || m) mod L ; S = (h a + r) mod L                               (:404-414)
         u64 pre[8], dg[8]; u32 w[16];
         le_limbs_to_be64(pre, enc);
@@ -160,7 +202,7 @@ k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, 
         sc_reduce512(h, w);
         sc_muladd(s, h, a, r);
     }
-    store8(sig64 + 64 * i, enc);
+    if (PHASE == 0) store8(sig64 + 64 * i, enc);
     store8(sig64 + 64 * i + 32, s);
 }
 
@@ -225,10 +267,11 @@ k_ed25519_verify_init(uint8_t* __restrict__ ctx, const uint8_t* __restrict__ pk3
     }
 }
 
+template <bool DEFER>
 __global__ void __launch_bounds__(kThreads)
 k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx, const uint32_t* __restrict__ key_index,
                        const uint8_t* __restrict__ sig64, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
-                       size_t fixed_len, size_t n, const u32* __restrict__ gtable)
+                       size_t fixed_len, size_t n, const u32* __restrict__ gtable, uint8_t* __restrict__ scratch)
 {
     C25519_COMB_SMEM;
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -270,6 +313,7 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
         load_pe(q, tab + 128 * comb4_index(h, j));
         ge_add_pe(S, S, q);
     }
+    if (DEFER) { store_xyz(scratch + kScratchXYZ * i, S); return; }     // k_normalize encodes and compares with R
     u32 enc[8];
     ge_encode(enc, S);
     u32 diff = 0;
@@ -281,27 +325,70 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
 // ---- launchers ----------------------------------------------------------------------------------
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
+// run `body(scratch)` with a stream-ordered scratch buffer of `bytes`
+template <typename Body>
+static cudaError_t with_scratch(size_t bytes, cudaStream_t s, Body body)
+{
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, bytes, s);
+    if (e != cudaSuccess) return e;
+    e = body(scratch);
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_x25519_comb(uint8_t* pk32, uint8_t* sk32_inout, size_t n, const uint32_t* table, cudaStream_t s)
 {
     if (!n) return cudaSuccess;
-    k_x25519_comb<<<grid_for(n), kThreads, 0, s>>>(pk32, sk32_inout, n, table);
-    count_launch();
-    return cudaGetLastError();
+    if (n < kDeferThreshold) {
+        k_x25519_comb<false><<<grid_for(n), kThreads, 0, s>>>(pk32, sk32_inout, n, table, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    return with_scratch(n * kScratchXZ, s, [&](uint8_t* scratch) {
+        k_x25519_comb<true><<<grid_for(n), kThreads, 0, s>>>(pk32, sk32_inout, n, table, scratch);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return launch_normalize(kNormX, scratch, kScratchXZ, n, pk32, 32, nullptr, 0, nullptr, 0, nullptr, s);
+    });
 }
 cudaError_t launch_ed25519_keypair(uint8_t* pub32, uint8_t* priv64, const uint8_t* seed32, size_t n, const uint32_t* table, cudaStream_t s)
 {
     if (!n) return cudaSuccess;
-    k_ed25519_keypair<<<grid_for(n), kThreads, 0, s>>>(pub32, priv64, seed32, n, table);
-    count_launch();
-    return cudaGetLastError();
+    if (n < kDeferThreshold) {
+        k_ed25519_keypair<false><<<grid_for(n), kThreads, 0, s>>>(pub32, priv64, seed32, n, table, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    return with_scratch(n * kScratchXYZ, s, [&](uint8_t* scratch) {
+        k_ed25519_keypair<true><<<grid_for(n), kThreads, 0, s>>>(pub32, priv64, seed32, n, table, scratch);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return launch_normalize(kNormEncode, scratch, kScratchXYZ, n, pub32, 32, priv64 + 32, 64, nullptr, 0, nullptr, s);
+    });
 }
 cudaError_t launch_ed25519_sign(uint8_t* sig64, const uint8_t* priv64, const uint8_t* msgs, const uint64_t* off, size_t fixed_len,
                                 size_t n, const uint32_t* table, cudaStream_t s)
 {
     if (!n) return cudaSuccess;
-    k_ed25519_sign<<<grid_for(n), kThreads, 0, s>>>(sig64, priv64, msgs, off, fixed_len, n, table);
-    count_launch();
-    return cudaGetLastError();
+    if (n < kDeferThreshold) {
+        k_ed25519_sign<0><<<grid_for(n), kThreads, 0, s>>>(sig64, priv64, msgs, off, fixed_len, n, table, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    return with_scratch(n * kSignScratch, s, [&](uint8_t* scratch) {
+        k_ed25519_sign<1><<<grid_for(n), kThreads, 0, s>>>(sig64, priv64, msgs, off, fixed_len, n, table, scratch);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch_normalize(kNormEncode, scratch, kSignScratch, n, sig64, 64, nullptr, 0, nullptr, 0, nullptr, s);
+        if (e != cudaSuccess) return e;
+        k_ed25519_sign<2><<<grid_for(n), kThreads, 0, s>>>(sig64, priv64, msgs, off, fixed_len, n, table, scratch);
+        count_launch();
+        return cudaGetLastError();
+    });
 }
 cudaError_t launch_ed25519_verify_init(uint8_t* ctx, const uint8_t* pk32, size_t n_keys, cudaStream_t s)
 {
@@ -315,9 +402,18 @@ cudaError_t launch_ed25519_verify_check(int32_t* ok, const uint8_t* ctx, const u
                                         const uint32_t* table, cudaStream_t s)
 {
     if (!n) return cudaSuccess;
-    k_ed25519_verify_check<<<grid_for(n), kThreads, 0, s>>>(ok, ctx, key_index, sig64, msgs, off, fixed_len, n, table);
-    count_launch();
-    return cudaGetLastError();
+    if (n < kDeferThreshold) {
+        k_ed25519_verify_check<false><<<grid_for(n), kThreads, 0, s>>>(ok, ctx, key_index, sig64, msgs, off, fixed_len, n, table, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    return with_scratch(n * kScratchXYZ, s, [&](uint8_t* scratch) {
+        k_ed25519_verify_check<true><<<grid_for(n), kThreads, 0, s>>>(ok, ctx, key_index, sig64, msgs, off, fixed_len, n, table, scratch);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        return launch_normalize(kNormCompare, scratch, kScratchXYZ, n, nullptr, 0, nullptr, 0, sig64, 64, ok, s);
+    });
 }
 
 // Single-phase verification = init + check over a stream-ordered workspace of 2080 B per item, processed in

@@ -496,6 +496,12 @@ C25519_DEV void fe_load(fe& z, const uint8_t* p)        // p 16-byte aligned
     uint4 a = __ldg(q), b = __ldg(q + 1);
     z.v[0] = a.x; z.v[1] = a.y; z.v[2] = a.z; z.v[3] = a.w; z.v[4] = b.x; z.v[5] = b.y; z.v[6] = b.z; z.v[7] = b.w;
 }
+C25519_DEV void fe_load_plain(fe& z, const uint8_t* p)  // coherent load (scratch written earlier in the same stream)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    z.v[0] = a.x; z.v[1] = a.y; z.v[2] = a.z; z.v[3] = a.w; z.v[4] = b.x; z.v[5] = b.y; z.v[6] = b.z; z.v[7] = b.w;
+}
 C25519_DEV void fe_store(uint8_t* p, const fe& z)
 {
     uint4* q = reinterpret_cast<uint4*>(p);

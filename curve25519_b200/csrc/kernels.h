@@ -27,6 +27,13 @@ cudaError_t launch_ed25519_verify_init(uint8_t* ctx, const uint8_t* pk32, size_t
 cudaError_t launch_ed25519_verify_check(int32_t* ok, const uint8_t* ctx, const uint32_t* key_index, const uint8_t* sig64,
                                         const uint8_t* msgs, const uint64_t* off, size_t fixed_len, size_t n,
                                         const uint32_t* table, cudaStream_t s);
+// Batched projective->affine conversion (normalize.cuh).  mode: 0 = X/Z -> out (stride out_stride),
+// 1 = encode(X/Z, Y/Z) -> out (and out2 if non-null), 2 = ok[i] = (encode == cmp[i]).  rec_stride = bytes per scratch record.
+cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size_t n, uint8_t* out, size_t out_stride,
+                             uint8_t* out2, size_t out2_stride, const uint8_t* cmp, size_t cmp_stride, int32_t* ok, cudaStream_t s);
+// below this many operations a batch is latency-bound and each kernel does its own inversion (one launch)
+constexpr size_t kDeferThreshold = 256;
+
 cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s);
 cudaError_t launch_imad_peak(uint64_t* mac_per_launch, uint32_t* sink, int iters, cudaStream_t s);
 

@@ -51,10 +51,11 @@ C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
     fe_mul(DZ, A, B);
 }
 
-// out = canonical x-coordinate of [k]u.   k must have bit 254 set and bit 255 clear (clamped);
-// kw(w) returns 32-bit word w of k.
+// (PX : PZ) = projective x-coordinate of [k]u.   k must have bit 254 set and bit 255 clear (clamped);
+// kw(w) returns 32-bit word w of k.  The affine result PX/PZ is produced later, for many operations at once,
+// by the batched inversion in normalize.cuh (PZ == 0 there yields 32 zero bytes like the reference).
 template <typename KeyWord>
-C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)
+C25519_DEV void x25519_ladder_projective(fe& PX, fe& PZ, const fe& u, KeyWord kw)
 {
     fe R0X, R0Z, R1X, R1Z;          // R0 = P, R1 = Q while `cur` is true
     fe_copy(R0X, u);
@@ -72,10 +73,16 @@ C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)
         cur = b;
         mont_step(R0X, R0Z, R1X, R1Z, u);    // bit = 1: P += Q, Q = 2Q ; bit = 0: Q += P, P = 2P
     }
-    fe PX, PZ;
     fe_select(PX, R1X, R0X, cur);
     fe_select(PZ, R1Z, R0Z, cur);
-    fe zi;
+}
+
+// out = canonical x-coordinate of [k]u (single-operation form: own inversion).
+template <typename KeyWord>
+C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)
+{
+    fe PX, PZ, zi;
+    x25519_ladder_projective(PX, PZ, u, kw);
     fe_invert(zi, PZ);
     fe_mul(out, PX, zi);
     fe_canon(out);

@@ -9,14 +9,20 @@
 // 128 B per operation (32 sk in, 32 sk clamped out, 32 pk in, 32 out) against ~150 k integer
 // multiply-adds, i.e. the kernel is bound by the integer pipes, not by HBM.
 #include "kernels.h"
+#include "normalize.cuh"
 #include "x25519.cuh"
 
 namespace c25519 {
 
 constexpr int kLadderThreads = 128;
 
+// DEFER = true : stop at the projective result, write (X, Z) to the 96-byte scratch record i; the affine
+//                result is produced for all operations by k_normalize (one shared inversion per 16 operations).
+// DEFER = false: finish in place with a private inversion (tiny, latency-bound batches; the n = 1 legacy calls).
+template <bool DEFER>
 __global__ void __launch_bounds__(kLadderThreads)
-k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n)
+k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n,
+                uint8_t* __restrict__ scratch)
 {
     __shared__ u32 ks[8][kLadderThreads];          // scalar words, one column per thread (conflict-free)
     const size_t i = (size_t)blockIdx.x * kLadderThreads + threadIdx.x;
@@ -35,19 +41,64 @@ k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, u
     fe u;
     if (pk32) fe_load(u, pk32 + 32 * i);           // all 256 bits (curve25519_dh.c:104)
     else fe_set_u32(u, 9);                         // ecp_BasePoint (curve25519_dh.c:37)
-    fe r;
     const int t = threadIdx.x;
-    x25519_ladder(r, u, [&](int w) { return ks[w][t]; });
-    fe_store(out32 + 32 * i, r);
+    if (DEFER) {
+        fe PX, PZ;
+        x25519_ladder_projective(PX, PZ, u, [&](int w) { return ks[w][t]; });
+        fe_store(scratch + kScratchXZ * i, PX);
+        fe_store(scratch + kScratchXZ * i + 32, PZ);
+    } else {
+        fe r;
+        x25519_ladder(r, u, [&](int w) { return ks[w][t]; });
+        fe_store(out32 + 32 * i, r);
+    }
+}
+
+// ---- batched normalisation kernel (shared by every operation of the path) ---------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_normalize(uint8_t* __restrict__ scratch, size_t rec_stride, size_t n, size_t nthreads, int K, uint8_t* __restrict__ out, size_t out_stride,
+            uint8_t* __restrict__ out2, size_t out2_stride, const uint8_t* __restrict__ cmp, size_t cmp_stride, int32_t* __restrict__ ok)
+{
+    const size_t tid = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (tid >= nthreads) return;
+    normalize_walk<MODE>(scratch, rec_stride, n, tid, nthreads, K, out, out_stride, out2, out2_stride, cmp, cmp_stride, ok);
+}
+
+cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size_t n, uint8_t* out, size_t out_stride,
+                             uint8_t* out2, size_t out2_stride, const uint8_t* cmp, size_t cmp_stride, int32_t* ok, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    size_t k = n / 32768; if (k < 1) k = 1; if (k > 16) k = 16;         // records walked per thread
+    const size_t nthreads = (n + k - 1) / k;
+    const unsigned grid = (unsigned)((nthreads + 127) / 128);
+    switch (mode) {
+    case kNormX: k_normalize<kNormX><<<grid, 128, 0, s>>>(scratch, rec_stride, n, nthreads, (int)k, out, out_stride, out2, out2_stride, cmp, cmp_stride, ok); break;
+    case kNormEncode: k_normalize<kNormEncode><<<grid, 128, 0, s>>>(scratch, rec_stride, n, nthreads, (int)k, out, out_stride, out2, out2_stride, cmp, cmp_stride, ok); break;
+    default: k_normalize<kNormCompare><<<grid, 128, 0, s>>>(scratch, rec_stride, n, nthreads, (int)k, out, out_stride, out2, out2_stride, cmp, cmp_stride, ok); break;
+    }
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
-    k_x25519_ladder<<<grid, kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n);
+    if (n < kDeferThreshold) {
+        k_x25519_ladder<false><<<grid, kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, n * kScratchXZ, s);
+    if (e != cudaSuccess) return e;
+    k_x25519_ladder<true><<<grid, kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n, scratch);
     count_launch();
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s);
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace c25519
