@@ -210,18 +210,21 @@ def test_primitive(op, a, b=None, out_rec=32):
     return out
 
 
-def imad_peak(iters=4096, repeats=5):
-    """Measured IMAD.WIDE.U32 rate of this device in MAC32/s (roofline denominator), best of `repeats`."""
-    sink = torch.zeros(4, dtype=torch.int32, device="cuda")
+def imad_peak(iters=20000, repeats=3, accumulate=False):
+    """Measured IMAD.WIDE.U32 rate of this device in MAC32/s, best of `repeats`.
+    accumulate=False: fresh form (Rc = RZ), the fastest form and the conservative roofline denominator;
+    accumulate=True : 64-bit-accumulator form, the one a multi-precision MAC actually needs."""
+    sink = torch.arange(64, dtype=torch.int32, device="cuda") * 0x01010101 + 12345
     macs = C.c_uint64(0)
     L = lib()
-    check(L.c25519_imad_peak_kernel(C.byref(macs), _p(sink), 64, _stream()), "imad_peak")
+    sign = -1 if accumulate else 1
+    check(L.c25519_imad_peak_kernel(C.byref(macs), _p(sink), sign * 2000, _stream()), "imad_peak")
     torch.cuda.synchronize()
     best = 0.0
     for _ in range(repeats):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(L.c25519_imad_peak_kernel(C.byref(macs), _p(sink), int(iters), _stream()), "imad_peak")
+        check(L.c25519_imad_peak_kernel(C.byref(macs), _p(sink), sign * int(iters), _stream()), "imad_peak")
         e1.record(); torch.cuda.synchronize()
         best = max(best, macs.value / (e0.elapsed_time(e1) * 1e-3))
     return best

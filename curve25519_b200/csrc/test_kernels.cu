@@ -72,40 +72,58 @@ cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// IMAD.WIDE.U32 peak: 8 independent 64-bit accumulator chains per thread, 32 multiply-accumulates per
-// loop trip, no memory traffic.  148 SMs x 4 resident CTAs x 256 threads.
+// IMAD.WIDE.U32 rate of this device, measured two ways (SASS of both loops checked with cuobjdump):
+//   form 0 "fresh"      : IMAD.WIDE.U32 Rd, Ra, Rb, RZ        (2 register reads)  -- the fastest form that exists;
+//                         this is the conservative roofline denominator bench.py reports against.
+//   form 1 "accumulate" : IMAD.WIDE.U32 Rd, Ra, Rb, Rd        (4 register reads: 64-bit accumulator)  -- the form a
+//                         multi-precision multiply-accumulate needs for ~3/4 of its products; measured at ~0.56x the
+//                         fresh rate on B200 (see profiles/r1_ubench4.txt), so it is the practical bound of fe_mul.
+// 8 independent products per loop trip, distinct operands (no operand-reuse cache hits), no memory traffic.
+// 148 SMs x 4 resident CTAs x 256 threads.
 constexpr int kPeakBlocks = 148 * 4;
 constexpr int kPeakThreads = 256;
 
+template <int FORM>
 __global__ void __launch_bounds__(kPeakThreads)
-k_imad_peak(uint32_t* sink, int iters)
+k_imad_peak(uint32_t* sink, const uint32_t* src, int iters)
 {
-    unsigned long long a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    u32 x = 0x9e3779b9u ^ threadIdx.x, y = 0x85ebca6bu + blockIdx.x;
+    const int t = blockIdx.x * kPeakThreads + threadIdx.x;
+    unsigned long long a0 = src[(t + 0) & 63], a1 = src[(t + 1) & 63], a2 = src[(t + 2) & 63], a3 = src[(t + 3) & 63],
+                       a4 = src[(t + 4) & 63], a5 = src[(t + 5) & 63], a6 = src[(t + 6) & 63], a7 = src[(t + 7) & 63];
+    u32 x0 = src[(t + 8) & 63] | 1, x1 = src[(t + 9) & 63] | 1, x2 = src[(t + 10) & 63] | 1, x3 = src[(t + 11) & 63] | 1,
+        x4 = src[(t + 12) & 63] | 1, x5 = src[(t + 13) & 63] | 1, x6 = src[(t + 14) & 63] | 1, x7 = src[(t + 15) & 63] | 1;
+    u32 y0 = src[(t + 16) & 63] | 1, y1 = src[(t + 17) & 63] | 1, y2 = src[(t + 18) & 63] | 1, y3 = src[(t + 19) & 63] | 1,
+        y4 = src[(t + 20) & 63] | 1, y5 = src[(t + 21) & 63] | 1, y6 = src[(t + 22) & 63] | 1, y7 = src[(t + 23) & 63] | 1;
+    u32 r0 = x0, r1 = x1, r2 = x2, r3 = x3, r4 = x4, r5 = x5, r6 = x6, r7 = x7;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\t"
-                         "mad.wide.u32 %1, %8, %9, %1;\n\t"
-                         "mad.wide.u32 %2, %8, %9, %2;\n\t"
-                         "mad.wide.u32 %3, %8, %9, %3;\n\t"
-                         "mad.wide.u32 %4, %8, %9, %4;\n\t"
-                         "mad.wide.u32 %5, %8, %9, %5;\n\t"
-                         "mad.wide.u32 %6, %8, %9, %6;\n\t"
-                         "mad.wide.u32 %7, %8, %9, %7;"
-                         : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
-                         : "r"(x), "r"(y));
+        unsigned long long p0, p1, p2, p3, p4, p5, p6, p7;
+        asm volatile("mul.wide.u32 %0,%8,%16; mul.wide.u32 %1,%9,%17; mul.wide.u32 %2,%10,%18; mul.wide.u32 %3,%11,%19; "
+                     "mul.wide.u32 %4,%12,%20; mul.wide.u32 %5,%13,%21; mul.wide.u32 %6,%14,%22; mul.wide.u32 %7,%15,%23;"
+                     : "=l"(p0), "=l"(p1), "=l"(p2), "=l"(p3), "=l"(p4), "=l"(p5), "=l"(p6), "=l"(p7)
+                     : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6), "r"(x7),
+                       "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(y4), "r"(y5), "r"(y6), "r"(y7));
+        if (FORM == 0) {        // consume the fresh products on the ALU pipe (one 3-input XOR each)
+            r0 ^= (u32)p0 ^ (u32)(p0 >> 32); r1 ^= (u32)p1 ^ (u32)(p1 >> 32); r2 ^= (u32)p2 ^ (u32)(p2 >> 32); r3 ^= (u32)p3 ^ (u32)(p3 >> 32);
+            r4 ^= (u32)p4 ^ (u32)(p4 >> 32); r5 ^= (u32)p5 ^ (u32)(p5 >> 32); r6 ^= (u32)p6 ^ (u32)(p6 >> 32); r7 ^= (u32)p7 ^ (u32)(p7 >> 32);
+        } else {                // ptxas folds these 64-bit adds into the multiply: IMAD.WIDE.U32 Rd, Ra, Rb, Rd
+            a0 += p0; a1 += p1; a2 += p2; a3 += p3; a4 += p4; a5 += p5; a6 += p6; a7 += p7;
         }
+        x0 += 1;                // keeps the products loop-variant
     }
     unsigned long long r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-    if (r == 0x1234567ull) sink[0] = (u32)r;      // never true in practice; keeps the chains alive
+    u32 q = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7 ^ x0;
+    if ((u32)r == 0x12345u && q == 77u) sink[0] = (u32)(r >> 32);      // never true in practice; keeps the chains alive
 }
 
 cudaError_t launch_imad_peak(uint64_t* mac_per_launch, uint32_t* sink, int iters, cudaStream_t s)
 {
-    if (mac_per_launch) *mac_per_launch = (uint64_t)kPeakBlocks * kPeakThreads * (uint64_t)iters * 32ull;
-    k_imad_peak<<<kPeakBlocks, kPeakThreads, 0, s>>>(sink, iters);
+    // iters < 0 selects the accumulate form (|iters| trips); sink must hold >= 64 words of arbitrary data
+    const int form = iters < 0 ? 1 : 0;
+    const int n = iters < 0 ? -iters : iters;
+    if (mac_per_launch) *mac_per_launch = (uint64_t)kPeakBlocks * kPeakThreads * (uint64_t)n * 8ull;
+    if (form) k_imad_peak<1><<<kPeakBlocks, kPeakThreads, 0, s>>>(sink, sink, n);
+    else k_imad_peak<0><<<kPeakBlocks, kPeakThreads, 0, s>>>(sink, sink, n);
     count_launch();
     return cudaGetLastError();
 }
