@@ -146,8 +146,8 @@ C25519_DEV void merge_cols(u32* a, const u32* b)
 }
 
 // ------------------------------------------------------------------ multiplication (ecp_MulReduce)
-// z = x*y mod (2^256-38), folded once more at bit 255.  Inputs W, output N.  z may alias x or y.
-C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y)
+// Schoolbook 8x8: 64 products.  z = x*y mod (2^256-38), folded once more at bit 255.  Inputs W, output N.
+C25519_DEV void fe_mul_schoolbook(fe& z, const fe& x, const fe& y)
 {
     const u32* a = x.v; const u32* b = y.v;
     u32 A[16], B[14];
@@ -167,6 +167,110 @@ C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y)
     merge_cols(A, B);
     reduce16(z, A);
 }
+
+// 4x4-limb product (128 x 128 -> 256 bits), same two-column-file scheme: 7 fresh + 9 accumulating IMAD.WIDE.
+//   out[0..7] = a[0..3] * b[0..3]
+C25519_DEV void mul4x4(u32* out, const u32* a, const u32* b)
+{
+    u32 B[6];                  // B[k] sits at word position k+1 (positions 1..6); `out` doubles as file A (0..7)
+    mul_wide(out[0], out[1], a[0], b[0]); mul_wide(out[2], out[3], a[2], b[0]);
+    mul_wide(B[0], B[1], a[1], b[0]);     mul_wide(B[2], B[3], a[3], b[0]);
+    // row 1: even limbs -> B cols 1,3 (accumulate, carry -> out[5]); odd limbs -> A col 2 (acc), col 4 (fresh)
+    asm("{\n\t"
+        "mad.lo.cc.u32  %0, %9, %12, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %12, 0;\n\t"  "madc.hi.u32    %3, %10, %12, 0;\n\t"
+        "mad.lo.cc.u32  %4, %8, %12, %4;\n\t"  "madc.hi.cc.u32 %5, %8, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t" "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "+r"(out[2]), "+r"(out[3]), "=&r"(out[4]), "=&r"(out[5]), "+r"(B[0]), "+r"(B[1]), "+r"(B[2]), "+r"(B[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[2]), "r"(b[1]));
+    // row 2: even limbs -> A cols 2,4 (acc, carry -> B[5]); odd limbs -> B col 3 (acc), col 5 (fresh)
+    asm("{\n\t"
+        "mad.lo.cc.u32  %0, %9, %12, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %12, 0;\n\t"  "madc.hi.u32    %3, %10, %12, 0;\n\t"
+        "mad.lo.cc.u32  %4, %8, %12, %4;\n\t"  "madc.hi.cc.u32 %5, %8, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t" "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "+r"(B[2]), "+r"(B[3]), "=&r"(B[4]), "=&r"(B[5]), "+r"(out[2]), "+r"(out[3]), "+r"(out[4]), "+r"(out[5])
+        : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[2]), "r"(b[2]));
+    // row 3: even limbs -> B cols 3,5 (acc, carry -> out[7]); odd limbs -> A col 4 (acc), col 6 (fresh)
+    asm("{\n\t"
+        "mad.lo.cc.u32  %0, %9, %12, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %12, 0;\n\t"  "madc.hi.u32    %3, %10, %12, 0;\n\t"
+        "mad.lo.cc.u32  %4, %8, %12, %4;\n\t"  "madc.hi.cc.u32 %5, %8, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t" "madc.hi.cc.u32 %7, %11, %12, %7;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "}"
+        : "+r"(out[4]), "+r"(out[5]), "=&r"(out[6]), "=&r"(out[7]), "+r"(B[2]), "+r"(B[3]), "+r"(B[4]), "+r"(B[5])
+        : "r"(a[0]), "r"(a[1]), "r"(a[3]), "r"(a[2]), "r"(b[3]));
+    // out[k] += B[k-1], k = 1..6, carry into out[7]
+    asm("add.cc.u32  %0, %0, %7;\n\t"
+        "addc.cc.u32 %1, %1, %8;\n\t"
+        "addc.cc.u32 %2, %2, %9;\n\t"
+        "addc.cc.u32 %3, %3, %10;\n\t"
+        "addc.cc.u32 %4, %4, %11;\n\t"
+        "addc.cc.u32 %5, %5, %12;\n\t"
+        "addc.u32    %6, %6, 0;"
+        : "+r"(out[1]), "+r"(out[2]), "+r"(out[3]), "+r"(out[4]), "+r"(out[5]), "+r"(out[6]), "+r"(out[7])
+        : "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]));
+}
+
+// One level of Karatsuba over 128-bit halves: 48 products instead of 64, and -- what matters on B200, where an
+// IMAD.WIDE with a 64-bit register accumulator issues at ~0.56x the rate of one with a zero accumulator
+// (profiles/r1_ubench4.txt) -- 21 fresh + 27 accumulating multiplies instead of 15 + 49.  The extra ~75
+// add/sub instructions go to the ALU pipe, which has slack in every kernel of this engine.
+//   x = xl + 2^128 xh, y = yl + 2^128 yh
+//   z0 = xl yl, z2 = xh yh, zm = (xl + xh)(yl + yh)  (129-bit sums: 4-limb product + carry-bit corrections)
+//   x y = z0 + 2^128 (zm - z0 - z2) + 2^256 z2
+C25519_DEV void fe_mul_karatsuba(fe& z, const fe& x, const fe& y)
+{
+    u32 T[16];                          // T[0..7] = z0, T[8..15] = z2
+    mul4x4(T, x.v, y.v);
+    mul4x4(T + 8, x.v + 4, y.v + 4);
+    u32 xs[4], ys[4], cx, cy;
+    asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, 0, 0;"
+        : "=&r"(xs[0]), "=&r"(xs[1]), "=&r"(xs[2]), "=&r"(xs[3]), "=&r"(cx)
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]));
+    asm("add.cc.u32 %0, %5, %9;\n\t addc.cc.u32 %1, %6, %10;\n\t addc.cc.u32 %2, %7, %11;\n\t addc.cc.u32 %3, %8, %12;\n\t addc.u32 %4, 0, 0;"
+        : "=&r"(ys[0]), "=&r"(ys[1]), "=&r"(ys[2]), "=&r"(ys[3]), "=&r"(cy)
+        : "r"(y.v[0]), "r"(y.v[1]), "r"(y.v[2]), "r"(y.v[3]), "r"(y.v[4]), "r"(y.v[5]), "r"(y.v[6]), "r"(y.v[7]));
+    u32 M[9];                           // zm = (xl+xh)(yl+yh) < 2^258: 9 words
+    mul4x4(M, xs, ys);
+    {   // carry-bit corrections: + cx * ys * 2^128 + cy * xs * 2^128 + cx cy 2^256
+        const u32 mx = 0u - cx, my = 0u - cy;
+        u32 p0 = ys[0] & mx, p1 = ys[1] & mx, p2 = ys[2] & mx, p3 = ys[3] & mx;
+        u32 q0 = xs[0] & my, q1 = xs[1] & my, q2 = xs[2] & my, q3 = xs[3] & my;
+        M[8] = cx & cy;
+        asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t addc.u32 %4, %4, 0;"
+            : "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8]) : "r"(p0), "r"(p1), "r"(p2), "r"(p3));
+        asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t addc.u32 %4, %4, 0;"
+            : "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8]) : "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+    }
+    // M -= z0; M -= z2    (the cross term xl yh + xh yl, 0 <= M < 2^257)
+    asm("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, %11;\n\t subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t subc.cc.u32 %5, %5, %14;\n\t subc.cc.u32 %6, %6, %15;\n\t subc.cc.u32 %7, %7, %16;\n\t subc.u32 %8, %8, 0;"
+        : "+r"(M[0]), "+r"(M[1]), "+r"(M[2]), "+r"(M[3]), "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8])
+        : "r"(T[0]), "r"(T[1]), "r"(T[2]), "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(T[6]), "r"(T[7]));
+    asm("sub.cc.u32 %0, %0, %9;\n\t subc.cc.u32 %1, %1, %10;\n\t subc.cc.u32 %2, %2, %11;\n\t subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t subc.cc.u32 %5, %5, %14;\n\t subc.cc.u32 %6, %6, %15;\n\t subc.cc.u32 %7, %7, %16;\n\t subc.u32 %8, %8, 0;"
+        : "+r"(M[0]), "+r"(M[1]), "+r"(M[2]), "+r"(M[3]), "+r"(M[4]), "+r"(M[5]), "+r"(M[6]), "+r"(M[7]), "+r"(M[8])
+        : "r"(T[8]), "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+    // T[4..12] += M, ripple into T[13..15]
+    asm("add.cc.u32 %0, %0, %12;\n\t addc.cc.u32 %1, %1, %13;\n\t addc.cc.u32 %2, %2, %14;\n\t addc.cc.u32 %3, %3, %15;\n\t"
+        "addc.cc.u32 %4, %4, %16;\n\t addc.cc.u32 %5, %5, %17;\n\t addc.cc.u32 %6, %6, %18;\n\t addc.cc.u32 %7, %7, %19;\n\t"
+        "addc.cc.u32 %8, %8, %20;\n\t addc.cc.u32 %9, %9, 0;\n\t addc.cc.u32 %10, %10, 0;\n\t addc.u32 %11, %11, 0;"
+        : "+r"(T[4]), "+r"(T[5]), "+r"(T[6]), "+r"(T[7]), "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(M[0]), "r"(M[1]), "r"(M[2]), "r"(M[3]), "r"(M[4]), "r"(M[5]), "r"(M[6]), "r"(M[7]), "r"(M[8]));
+    reduce16(z, T);
+}
+
+#ifndef C25519_MUL_SCHOOLBOOK
+C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y) { fe_mul_karatsuba(z, x, y); }
+#else
+C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y) { fe_mul_schoolbook(z, x, y); }
+#endif
 
 // ------------------------------------------------------------------ squaring (ecp_SqrReduce)
 // 28 off-diagonal products (two column files as in fe_mul), doubled, plus 8 diagonal squares.  Output N.

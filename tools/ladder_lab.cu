@@ -77,19 +77,10 @@ int main(int argc,char**argv){
     for(size_t i=0;i<32*c.n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; h[i]=(uint8_t)(s>>24);} cudaMemcpy(c.pk,h.data(),32*c.n,cudaMemcpyHostToDevice);
     for(size_t i=0;i<32*c.n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; h[i]=(uint8_t)(s>>24);} cudaMemcpy(c.sk,h.data(),32*c.n,cudaMemcpyHostToDevice);
     timeit("T128 min1 (ptxas free)", k_ladder<128,1>,128,c.n,c,true);
-    timeit("T128 min3 (<=168 regs)", k_ladder<128,3>,128,c.n,c,false);
     timeit("T128 min4 (<=128 regs)", k_ladder<128,4>,128,c.n,c,false);
     timeit("T128 min5 (<=96 regs)",  k_ladder<128,5>,128,c.n,c,false);
     timeit("T128 min6 (<=80 regs)",  k_ladder<128,6>,128,c.n,c,false);
-    timeit("T128 min7 (<=72 regs)",  k_ladder<128,7>,128,c.n,c,false);
-    timeit("T128 min8 (<=64 regs)",  k_ladder<128,8>,128,c.n,c,false);
-    timeit("T64  min10",             k_ladder<64,10>,64,c.n,c,false);
+    timeit("T64  min8",              k_ladder<64,8>,64,c.n,c,false);
     timeit("T256 min2",              k_ladder<256,2>,256,c.n,c,false);
-    timeit("T256 min3",              k_ladder<256,3>,256,c.n,c,false);
-    timeit("T32  min16",             k_ladder<32,16>,32,c.n,c,false);
-    timeit("ILP2 T128 min2",         k_ladder2<128,2>,128,(c.n+1)/2,c,false);
-    timeit("ILP2 T128 min3",         k_ladder2<128,3>,128,(c.n+1)/2,c,false);
-    timeit("ILP2 T64 min4",          k_ladder2<64,4>,64,(c.n+1)/2,c,false);
-    timeit("ILP2 T64 min6",          k_ladder2<64,6>,64,(c.n+1)/2,c,false);
     return 0;
 }

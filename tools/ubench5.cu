@@ -1,0 +1,62 @@
+// tools/ubench5.cu -- does the FP64 pipe run concurrently with the integer-multiply pipe on B200?
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#define CHK(x) do{cudaError_t e=(x); if(e){printf("ERR %s: %s\n",#x,cudaGetErrorString(e)); return 1;}}while(0)
+typedef uint32_t u32; typedef unsigned long long u64;
+template<int MODE>
+__global__ void __launch_bounds__(256) k(u32* sink, const u32* src, int iters, u64* cyc)
+{
+    const int t=blockIdx.x*256+threadIdx.x;
+    u64 a0=src[(t+0)&63],a1=src[(t+1)&63],a2=src[(t+2)&63],a3=src[(t+3)&63],a4=src[(t+4)&63],a5=src[(t+5)&63],a6=src[(t+6)&63],a7=src[(t+7)&63];
+    u32 x0=src[(t+8)&63]|1,x1=src[(t+9)&63]|1,x2=src[(t+10)&63]|1,x3=src[(t+11)&63]|1,x4=src[(t+12)&63]|1,x5=src[(t+13)&63]|1,x6=src[(t+14)&63]|1,x7=src[(t+15)&63]|1;
+    u32 y0=src[(t+16)&63]|1,y1=src[(t+17)&63]|1,y2=src[(t+18)&63]|1,y3=src[(t+19)&63]|1,y4=src[(t+20)&63]|1,y5=src[(t+21)&63]|1,y6=src[(t+22)&63]|1,y7=src[(t+23)&63]|1;
+    double d0=x0*1e-9,d1=x1*1e-9,d2=x2*1e-9,d3=x3*1e-9,d4=x4*1e-9,d5=x5*1e-9,d6=x6*1e-9,d7=x7*1e-9;
+    double e0=y0*1e-10,e1=y1*1e-10,e2=y2*1e-10,e3=y3*1e-10,e4=y4*1e-10,e5=y5*1e-10,e6=y6*1e-10,e7=y7*1e-10, f=0.999999;
+    u64 g0; asm volatile("mov.u64 %0, %%globaltimer;":"=l"(g0)); u64 t0=clock64();
+    #pragma unroll 1
+    for(int it=0;it<iters;it++){
+        if(MODE==0||MODE==2){
+            u64 p0,p1,p2,p3,p4,p5,p6,p7;
+            asm volatile("mul.wide.u32 %0,%8,%16; mul.wide.u32 %1,%9,%17; mul.wide.u32 %2,%10,%18; mul.wide.u32 %3,%11,%19; mul.wide.u32 %4,%12,%20; mul.wide.u32 %5,%13,%21; mul.wide.u32 %6,%14,%22; mul.wide.u32 %7,%15,%23;"
+              :"=l"(p0),"=l"(p1),"=l"(p2),"=l"(p3),"=l"(p4),"=l"(p5),"=l"(p6),"=l"(p7):"r"(x0),"r"(x1),"r"(x2),"r"(x3),"r"(x4),"r"(x5),"r"(x6),"r"(x7),"r"(y0),"r"(y1),"r"(y2),"r"(y3),"r"(y4),"r"(y5),"r"(y6),"r"(y7));
+            a0+=p0;a1+=p1;a2+=p2;a3+=p3;a4+=p4;a5+=p5;a6+=p6;a7+=p7; x0+=1;
+        }
+        if(MODE==1||MODE==2){
+            asm volatile("fma.rn.f64 %0,%0,%16,%8; fma.rn.f64 %1,%1,%16,%9; fma.rn.f64 %2,%2,%16,%10; fma.rn.f64 %3,%3,%16,%11; fma.rn.f64 %4,%4,%16,%12; fma.rn.f64 %5,%5,%16,%13; fma.rn.f64 %6,%6,%16,%14; fma.rn.f64 %7,%7,%16,%15;"
+              :"+d"(d0),"+d"(d1),"+d"(d2),"+d"(d3),"+d"(d4),"+d"(d5),"+d"(d6),"+d"(d7):"d"(e0),"d"(e1),"d"(e2),"d"(e3),"d"(e4),"d"(e5),"d"(e6),"d"(e7),"d"(f));
+        }
+        if(MODE==3){ // 16 DFMA per trip (more ILP)
+            asm volatile("fma.rn.f64 %0,%0,%16,%8; fma.rn.f64 %1,%1,%16,%9; fma.rn.f64 %2,%2,%16,%10; fma.rn.f64 %3,%3,%16,%11; fma.rn.f64 %4,%4,%16,%12; fma.rn.f64 %5,%5,%16,%13; fma.rn.f64 %6,%6,%16,%14; fma.rn.f64 %7,%7,%16,%15;\n\t"
+                         "fma.rn.f64 %8,%8,%16,%0; fma.rn.f64 %9,%9,%16,%1; fma.rn.f64 %10,%10,%16,%2; fma.rn.f64 %11,%11,%16,%3; fma.rn.f64 %12,%12,%16,%4; fma.rn.f64 %13,%13,%16,%5; fma.rn.f64 %14,%14,%16,%6; fma.rn.f64 %15,%15,%16,%7;"
+              :"+d"(d0),"+d"(d1),"+d"(d2),"+d"(d3),"+d"(d4),"+d"(d5),"+d"(d6),"+d"(d7),"+d"(e0),"+d"(e1),"+d"(e2),"+d"(e3),"+d"(e4),"+d"(e5),"+d"(e6),"+d"(e7):"d"(f));
+        }
+    }
+    u64 t1=clock64(); u64 g1; asm volatile("mov.u64 %0, %%globaltimer;":"=l"(g1));
+    u64 r=a0^a1^a2^a3^a4^a5^a6^a7; double ds=d0+d1+d2+d3+d4+d5+d6+d7+e0+e1+e2+e3+e4+e5+e6+e7;
+    if((u32)r==0x12345u && ds==77.0) sink[0]=(u32)(r>>32)+x0;
+    if(threadIdx.x==0&&blockIdx.x==0){cyc[0]=t1-t0;cyc[1]=g1-g0;}
+}
+template<int MODE> int run(const char* name,int bps,u32*sink,u32*src,u64*cyc)
+{
+    int iters=20000; int maxb=0; cudaFuncAttributes fa; cudaFuncGetAttributes(&fa,k<MODE>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb,k<MODE>,256,0); if(bps>maxb)bps=maxb; int grid=148*bps;
+    k<MODE><<<grid,256>>>(sink,src,4000,cyc); CHK(cudaDeviceSynchronize());
+    cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0); k<MODE><<<grid,256>>>(sink,src,iters,cyc); cudaEventRecord(e1); CHK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms,e0,e1); u64 c[2]; cudaMemcpy(c,cyc,16,cudaMemcpyDeviceToHost);
+    double f=(double)c[0]/(double)c[1]; double wps=bps*2.0; double per_trip=(double)ms*1e6*f/((double)iters*wps);
+    printf("%-44s regs=%3d w/SMSP=%4.1f cycles/trip/SMSP=%7.2f  clk=%.0f MHz\n",name,fa.numRegs,wps,per_trip,f*1e3);
+    return 0;
+}
+int main(){
+    u32*sink,*src; u64*cyc; CHK(cudaMalloc(&sink,64)); CHK(cudaMalloc(&cyc,64)); CHK(cudaMalloc(&src,4096));
+    u32 h[1024]; for(int i=0;i<1024;i++) h[i]=0x9e3779b9u*(i+1)^(0x85ebca6bu*(i*i+7)); cudaMemcpy(src,h,4096,cudaMemcpyHostToDevice);
+    for(int b: {2,4,8}){
+        run<0>("8 IMAD.WIDE accumulate",b,sink,src,cyc);
+        run<1>("8 DFMA",b,sink,src,cyc);
+        run<3>("16 DFMA",b,sink,src,cyc);
+        run<2>("8 IMAD.WIDE accumulate + 8 DFMA (same warp)",b,sink,src,cyc);
+    }
+    return 0;
+}
