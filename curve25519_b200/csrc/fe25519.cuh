@@ -217,10 +217,10 @@ C25519_DEV void mul4x4(u32* out, const u32* a, const u32* b)
         : "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]));
 }
 
-// One level of Karatsuba over 128-bit halves: 48 products instead of 64, and -- what matters on B200, where an
-// IMAD.WIDE with a 64-bit register accumulator issues at ~0.56x the rate of one with a zero accumulator
-// (profiles/r1_ubench4.txt) -- 21 fresh + 27 accumulating multiplies instead of 15 + 49.  The extra ~75
-// add/sub instructions go to the ALU pipe, which has slack in every kernel of this engine.
+// One level of Karatsuba over 128-bit halves (EXPERIMENT, not the default -- see the note at fe_mul below):
+// 48 products instead of 64, and 21 fresh + 27 accumulating multiplies instead of 15 + 49 (on B200 an IMAD.WIDE
+// with a 64-bit register accumulator issues at ~0.56x the rate of one with a zero accumulator,
+// profiles/r1_ubench4.txt), at the price of ~75 extra add/sub instructions.
 //   x = xl + 2^128 xh, y = yl + 2^128 yh
 //   z0 = xl yl, z2 = xh yh, zm = (xl + xh)(yl + yh)  (129-bit sums: 4-limb product + carry-bit corrections)
 //   x y = z0 + 2^128 (zm - z0 - z2) + 2^256 z2
@@ -266,7 +266,11 @@ C25519_DEV void fe_mul_karatsuba(fe& z, const fe& x, const fe& y)
     reduce16(z, T);
 }
 
-#ifndef C25519_MUL_SCHOOLBOOK
+// Measured on B200 (profiles/r1_ladder_lab_karatsuba_vs_schoolbook.txt): the Karatsuba variant is 3-4 % SLOWER in
+// the ladder (48.7-49.1 vs 50.7-50.9 M ops/s): ptxas places a good part of the extra additions and register
+// moves on the multiply pipe (IMAD.X / IMAD.MOV / IMAD.IADD), which eats the 16 saved products.  Schoolbook
+// is therefore the default; -DC25519_MUL_KARATSUBA selects the other (same tests, same results).
+#ifdef C25519_MUL_KARATSUBA
 C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y) { fe_mul_karatsuba(z, x, y); }
 #else
 C25519_DEV void fe_mul(fe& z, const fe& x, const fe& y) { fe_mul_schoolbook(z, x, y); }
