@@ -238,7 +238,7 @@ def main():
     pk_json = _peaks()
     hbm_peak = pk_json.get("hbm_gbs", 6650.0)
     hbm_ach = n * HBM_BYTES_PER_OP["x25519_shared"] / (kms * 1e-3) / 1e9
-    traffic = None
+    traffic = None                                  # dram__bytes_read.sum + dram__bytes_write.sum of the ladder kernel (ncu --set full)
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ladder_traffic.json")))["dram_bytes_per_op"] * n
     except Exception:
@@ -282,7 +282,7 @@ def main():
         e2e_s = float(t.item())
     e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "ops/s", "h2d_bytes_per_step": 64 * n, "d2h_bytes_per_step": 64 * n,
            "steps": e2e_steps, "api": "c25519_x25519_shared_host (pinned host buffers; H2D + ladder kernel + D2H per step, "
-                                     "4 pipelined slices on 2 streams)"}
+                                     "8 pipelined slices of 2^17 ops rotating over 4 streams)"}
 
     # ---- secondary metrics (N = 1): the other operations of the path on the same batch size
     secondary = None
@@ -301,7 +301,37 @@ def main():
             sms = time_steps(fn, ssteps, 1, None, torch) / ssteps
             ops = n / (sms * 1e-3)
             secondary[name] = {"value": ops, "unit": "ops/s", "ms_per_step": sms, "msg_bytes": 64 if "ed25519" in name else None,
-                               "imad_frac": ops * MAC32_PER_OP[name] / peak}
+                               "mac32_per_op": MAC32_PER_OP[name], "imad_frac": ops * MAC32_PER_OP[name] / peak,
+                               "imad_frac_of_accumulate_form": ops * MAC32_PER_OP[name] / peak_acc}
+
+    # ---- BASELINE config 5: mixed batch (1/2 X25519 shared keys, 1/4 Ed25519 sign, 1/4 verify) sharded over the ranks,
+    #      results packed into uniform 64-byte records, ONE all-gather per step
+    mixed = None
+    if not args.no_secondary:
+        nx, ns, nv = n // 2, n // 4, n // 4
+        seeds_m = d_sk[3][:ns + nv].contiguous()
+        msgs_m = torch.from_numpy(rng.integers(0, 256, (ns + nv, 64), dtype=np.uint8)).cuda()
+        pub_m, priv_m = api.ed25519_keypair(seeds_m)
+        sig_v = api.ed25519_sign(priv_m[ns:].contiguous(), msgs_m[ns:].contiguous())
+        priv_s, msgs_s = priv_m[:ns].contiguous(), msgs_m[:ns].contiguous()
+        pub_v, msgs_v = pub_m[ns:].contiguous(), msgs_m[ns:].contiguous()
+        rec = torch.zeros((nx + ns + nv, 64), dtype=torch.uint8, device="cuda")
+        gathered_m = torch.empty((world * (nx + ns + nv), 64), dtype=torch.uint8, device="cuda") if world > 1 else None
+        skx, pkx, outx = d_sk[0][:nx].contiguous(), d_pk[0][:nx].contiguous(), torch.empty((nx, 32), dtype=torch.uint8, device="cuda")
+
+        def mixed_step():
+            api.x25519_shared(pkx, skx, out=outx, sk_inplace=True)
+            rec[:nx, :32] = outx
+            rec[nx:nx + ns] = api.ed25519_sign(priv_s, msgs_s)
+            ok = api.ed25519_verify(sig_v, pub_v, msgs_v)
+            rec[nx + ns:, :4] = ok.view(torch.uint8).view(nv, 4)
+            if dist is not None:
+                dist.all_gather_into_tensor(gathered_m, rec)
+        msteps = max(3, min(args.steps, 5))
+        mms = time_steps(mixed_step, msteps, 1, dist, torch) / msteps
+        mixed = {"value": world * (nx + ns + nv) / (mms * 1e-3), "unit": "ops/s", "ms_per_step": mms,
+                 "ops_per_gpu_per_step": {"x25519_shared": nx, "ed25519_sign": ns, "ed25519_verify": nv},
+                 "collective": "one all_gather_into_tensor of 64-byte result records per step" if world > 1 else "none (single GPU)"}
 
     if rank == 0:
         threads = os.cpu_count() or 1
@@ -318,6 +348,8 @@ def main():
                 "speedup_vs_cpu_baseline": {"kernel": value / cpu["value"], "e2e": e2e["value"] / cpu["value"]}}
         if secondary is not None:
             line["secondary"] = secondary
+        if mixed is not None:
+            line["mixed_config5"] = mixed
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

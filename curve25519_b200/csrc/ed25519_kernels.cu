@@ -53,16 +53,24 @@ C25519_DEV void stage_comb_table(u32* smem_table, unsigned long long* bar, const
     __shared__ __align__(8) unsigned long long s_bar;                 \
     stage_comb_table(s_table, &s_bar, gtable)
 
-C25519_DEV void load8(u32 (&w)[8], const uint8_t* p)       // 16-byte aligned 32-byte record
+C25519_DEV void load8(u32 (&w)[8], const uint8_t* p)       // 32-byte record, one 256-bit load
 {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    fe t; fe_load(t, p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = t.v[i];
+}
+C25519_DEV void load8_plain(u32 (&w)[8], const uint8_t* p)
+{
+    fe t; fe_load_plain(t, p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = t.v[i];
 }
 C25519_DEV void store8(uint8_t* p, const u32 (&w)[8])
 {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(w[0], w[1], w[2], w[3]); q[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    fe t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t.v[i] = w[i];
+    fe_store(p, t);
 }
 C25519_DEV void clamp(u32 (&k)[8]) { k[0] &= 0xfffffff8u; k[7] = (k[7] | 0x40000000u) & 0x7fffffffu; }   // ecp_TrimSecretKey
 
@@ -81,8 +89,7 @@ k_x25519_comb(uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n, 
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     u32 k[8];
-    { const uint4* q = reinterpret_cast<const uint4*>(sk32 + 32 * i); uint4 a = q[0], b = q[1];
-      k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w; }
+    load8_plain(k, sk32 + 32 * i);
     clamp(k);
     store8(sk32 + 32 * i, k);
     ge_ext S;
@@ -183,13 +190,9 @@ k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, 
         }
         ge_encode(enc, S);
     } else {
-        const uint4* q = reinterpret_cast<const uint4*>(sig64 + 64 * i);     // plain loads: written by earlier launches
-        uint4 e0 = q[0], e1 = q[1], r0 = q[2], r1 = q[3];
-        enc[0] = e0.x; enc[1] = e0.y; enc[2] = e0.z; enc[3] = e0.w; enc[4] = e1.x; enc[5] = e1.y; enc[6] = e1.z; enc[7] = e1.w;
-        r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-        const uint4* qa = reinterpret_cast<const uint4*>(scratch + (size_t)kSignScratch * i + 128);
-        uint4 a0 = qa[0], a1 = qa[1];
-        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        load8_plain(enc, sig64 + 64 * i);                       // plain loads: written by earlier launches
+        load8_plain(r, sig64 + 64 * i + 32);
+        load8_plain(a, scratch + (size_t)kSignScratch * i + 128);
     }
     u32 pk[8], h[8], s[8];
     load8(pk, priv64 + 64 * i + 32);
@@ -209,14 +212,9 @@ k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, 
 // ---- verification ----------------------------------------------------------------------------------
 C25519_DEV void store_pe(uint8_t* p, const ge_pe& q)
 { fe_store(p, q.ypx); fe_store(p + 32, q.ymx); fe_store(p + 64, q.t2d); fe_store(p + 96, q.z2); }
-C25519_DEV void load_pe(ge_pe& q, const uint8_t* p)
-{
-    const uint4* e = reinterpret_cast<const uint4*>(p);
-    uint4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = e[k];        // plain loads: the table may have been written by this launch's predecessor
-    auto put = [](fe& f, uint4 a, uint4 b) { f.v[0] = a.x; f.v[1] = a.y; f.v[2] = a.z; f.v[3] = a.w; f.v[4] = b.x; f.v[5] = b.y; f.v[6] = b.z; f.v[7] = b.w; };
-    put(q.ypx, v[0], v[1]); put(q.ymx, v[2], v[3]); put(q.t2d, v[4], v[5]); put(q.z2, v[6], v[7]);
+C25519_DEV void load_pe(ge_pe& q, const uint8_t* p)        // 128-byte table entry: four 256-bit loads (coherent: the table
+{                                                           // may have been written by this launch's predecessor)
+    fe_load_plain(q.ypx, p); fe_load_plain(q.ymx, p + 32); fe_load_plain(q.t2d, p + 64); fe_load_plain(q.z2, p + 96);
 }
 
 // ctx record: [0,32) public key bytes, [32 + 128 j, 32 + 128 (j+1)) table entry j = sum_{k in bits(j)} 2^(64k) (-A)
@@ -285,8 +283,7 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
     load8(s, sig64 + 64 * i + 32);                              // S is used raw, all 256 bits     (:308)
     {   // h = H(enc(R) || pk || m) mod L                                                        (:298-304)
         u32 pk[8];
-        { const uint4* q = reinterpret_cast<const uint4*>(rec); uint4 a = q[0], b = q[1];
-          pk[0] = a.x; pk[1] = a.y; pk[2] = a.z; pk[3] = a.w; pk[4] = b.x; pk[5] = b.y; pk[6] = b.z; pk[7] = b.w; }
+        load8_plain(pk, rec);
         u64 pre[8], dg[8]; u32 w[16];
         le_limbs_to_be64(pre, R);
         le_limbs_to_be64(pre + 4, pk);

@@ -2,7 +2,7 @@
 //
 // Responsibilities: device selection and one-time upload of the comb table, argument checking, the
 // device-pointer batch entry points (thin: one kernel launch each, asynchronous on the caller's
-// stream), the host-pointer entry points (chunked, double-buffered H2D -> kernel -> D2H pipeline on two
+// stream), the host-pointer entry points (sliced H2D -> kernel -> D2H pipeline rotating over four
 // private streams, copying straight from/to the caller's buffers), and the reference's 11-function API as n = 1 batches.
 // There is no CPU implementation of any operation in this library: if CUDA is unusable every call fails.
 #include <cuda_runtime.h>
@@ -32,13 +32,14 @@ int g_device = -1;
 std::atomic<uint64_t> g_launches{0};
 thread_local char t_err[256] = "";
 
-// host-pointer pipeline resources (grow-only): two stages, each a private stream + device scratch
-constexpr size_t kChunkOps = 1u << 18;             // operations per pipeline stage
+// host-pointer pipeline resources (grow-only): kStages stages, each a private stream + device scratch
+constexpr size_t kChunkOps = 1u << 17;             // operations per pipeline slice
+constexpr int kStages = 4;                          // slices in flight (one private stream each)
 struct Stage {
     cudaStream_t stream = nullptr;
     uint8_t* dev = nullptr;  size_t dev_cap = 0;
 };
-Stage g_stage[2];
+Stage g_stage[kStages];
 
 int fail(int code, const char* what)
 {
@@ -99,8 +100,8 @@ struct Field { size_t rec; bool in, out; const uint8_t* src; uint8_t* dst; };
 
 // Generic chunked pipeline.  For each chunk: H2D the `in` fields straight from the caller's buffers
 // (truly asynchronous when they are pinned, driver-staged when pageable), run `launch` on the device
-// copies, D2H the `out` fields straight into the caller's buffers.  Two stages on two streams alternate,
-// so chunk c+1's H2D overlaps chunk c's kernel and chunk c-1's D2H; stream order protects the reuse of a
+// copies, D2H the `out` fields straight into the caller's buffers.  kStages stages on as many streams rotate,
+// so slice c+1's H2D overlaps slice c's kernel and slice c-1's D2H (both PCIe directions busy); stream order protects the reuse of a
 // stage's device scratch.  Returns after both streams have drained.
 template <int NF, typename Launch>
 int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
@@ -114,7 +115,7 @@ int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
     for (int k = 0; k < NF; k++) offs[k + 1] = offs[k] + align_up(f[k].rec * chunk, 256);
     for (auto& st : g_stage) if (int rc = reserve(st, offs[NF])) return rc;
     int s = 0;
-    for (size_t base = 0; base < n; base += chunk, s ^= 1) {
+    for (size_t base = 0; base < n; base += chunk, s = (s + 1) % kStages) {
         const size_t cnt = std::min(chunk, n - base);
         Stage& st = g_stage[s];
         uint8_t* d[NF];
@@ -126,10 +127,11 @@ int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
         for (int k = 0; k < NF; k++)
             if (f[k].out) CK(cudaMemcpyAsync(f[k].dst + f[k].rec * base, d[k], f[k].rec * cnt, cudaMemcpyDeviceToHost, st.stream));
     }
-    CK(cudaStreamSynchronize(g_stage[0].stream));
-    CK(cudaStreamSynchronize(g_stage[1].stream));
+    for (auto& st : g_stage) CK(cudaStreamSynchronize(st.stream));
     return 0;
 }
+
+inline bool misaligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) != 0; }
 
 int check_ready()
 {
@@ -184,6 +186,7 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
 {
     if (int rc = check_ready()) return rc;
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(out32) || misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_x25519_ladder(out32, pk32, sk32_inout, n, (cudaStream_t)stream));
     return 0;
 }
@@ -192,6 +195,7 @@ int c25519_x25519_public_batch(uint8_t* pk32, uint8_t* sk32_inout, size_t n, int
 {
     if (int rc = check_ready()) return rc;
     if (n && (!pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     if (ladder) CK(launch_x25519_ladder(pk32, nullptr, sk32_inout, n, (cudaStream_t)stream));
     else CK(launch_x25519_comb(pk32, sk32_inout, n, g_comb_table_dev, (cudaStream_t)stream));
     return 0;
@@ -201,6 +205,7 @@ int c25519_ed25519_keypair_batch(uint8_t* pub32, uint8_t* priv64, const uint8_t*
 {
     if (int rc = check_ready()) return rc;
     if (n && (!pub32 || !priv64 || !seed32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(pub32) || misaligned32(priv64) || misaligned32(seed32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_ed25519_keypair(pub32, priv64, seed32, n, g_comb_table_dev, (cudaStream_t)stream));
     return 0;
 }
@@ -210,6 +215,7 @@ int c25519_ed25519_sign_batch(uint8_t* sig64, const uint8_t* priv64, const uint8
 {
     if (int rc = check_ready()) return rc;
     if (n && (!sig64 || !priv64)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(sig64) || misaligned32(priv64)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_ed25519_sign(sig64, priv64, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
     return 0;
 }
@@ -219,6 +225,7 @@ int c25519_ed25519_verify_batch(int32_t* ok, const uint8_t* sig64, const uint8_t
 {
     if (int rc = check_ready()) return rc;
     if (n && (!ok || !sig64 || !pk32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(sig64) || misaligned32(pk32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_ed25519_verify(ok, sig64, pk32, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
     return 0;
 }
@@ -227,6 +234,7 @@ int c25519_ed25519_verify_init_batch(uint8_t* ctx, const uint8_t* pk32, size_t n
 {
     if (int rc = check_ready()) return rc;
     if (n_keys && (!ctx || !pk32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(ctx) || misaligned32(pk32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_ed25519_verify_init(ctx, pk32, n_keys, (cudaStream_t)stream));
     return 0;
 }
@@ -236,6 +244,7 @@ int c25519_ed25519_verify_check_batch(int32_t* ok, const uint8_t* ctx, const uin
 {
     if (int rc = check_ready()) return rc;
     if (n && (!ok || !ctx || !sig64)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(ctx) || misaligned32(sig64)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_ed25519_verify_check(ok, ctx, key_index, sig64, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
     return 0;
 }

@@ -597,24 +597,26 @@ C25519_DEV void fe_pow22523(fe& out, const fe& z)
 { fe t, z11; fe_pow_2_250_1(t, z11, z); fe_sqr_n(t, t, 2); fe_mul(out, t, z); }
 
 // ------------------------------------------------------------------ byte codecs (little-endian host == limb order)
-// ecp_BytesToWords curve25519_utils.c:43 / ecp_WordsToBytes :61: a 32-byte record IS the limb array.
-C25519_DEV void fe_load(fe& z, const uint8_t* p)        // p 16-byte aligned
+// ecp_BytesToWords curve25519_utils.c:43 / ecp_WordsToBytes :61: a 32-byte record IS the limb array, and
+// sm_100 moves it with ONE 256-bit access per thread (PTX ld/st.global.v8.b32, SASS LDG/STG.E.ENL2.256).
+// Records must be 32-byte aligned (checked at the C ABI).
+C25519_DEV void fe_load(fe& z, const uint8_t* p)        // read-only input (non-coherent path)
 {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
-    z.v[0] = a.x; z.v[1] = a.y; z.v[2] = a.z; z.v[3] = a.w; z.v[4] = b.x; z.v[5] = b.y; z.v[6] = b.z; z.v[7] = b.w;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(z.v[0]), "=r"(z.v[1]), "=r"(z.v[2]), "=r"(z.v[3]), "=r"(z.v[4]), "=r"(z.v[5]), "=r"(z.v[6]), "=r"(z.v[7])
+                 : "l"(p));
 }
-C25519_DEV void fe_load_plain(fe& z, const uint8_t* p)  // coherent load (scratch written earlier in the same stream)
+C25519_DEV void fe_load_plain(fe& z, const uint8_t* p)  // coherent load (data written earlier by this grid or stream)
 {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = q[0], b = q[1];
-    z.v[0] = a.x; z.v[1] = a.y; z.v[2] = a.z; z.v[3] = a.w; z.v[4] = b.x; z.v[5] = b.y; z.v[6] = b.z; z.v[7] = b.w;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(z.v[0]), "=r"(z.v[1]), "=r"(z.v[2]), "=r"(z.v[3]), "=r"(z.v[4]), "=r"(z.v[5]), "=r"(z.v[6]), "=r"(z.v[7])
+                 : "l"(p) : "memory");
 }
 C25519_DEV void fe_store(uint8_t* p, const fe& z)
 {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(z.v[0], z.v[1], z.v[2], z.v[3]);
-    q[1] = make_uint4(z.v[4], z.v[5], z.v[6], z.v[7]);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(z.v[0]), "r"(z.v[1]), "r"(z.v[2]), "r"(z.v[3]), "r"(z.v[4]), "r"(z.v[5]), "r"(z.v[6]), "r"(z.v[7])
+                 : "memory");
 }
 
 }  // namespace c25519

@@ -4,8 +4,8 @@
 //                     curve25519_dh_CalculatePublicKey (:192); one operation per thread.
 //
 // Data layout in HBM: three arrays of 32-byte records (scalars in/out, peer points in, results out),
-// record i belongs to thread i.  Each thread moves its record with two 16-byte vector accesses; a warp
-// therefore touches one contiguous, 128-byte-aligned 1 KB span per array.  Algorithmic HBM traffic is
+// record i belongs to thread i.  Each thread moves its record with ONE 256-bit access (LDG/STG.E.ENL2.256); a warp
+// therefore touches one contiguous 1 KB span per array.  Algorithmic HBM traffic is
 // 128 B per operation (32 sk in, 32 sk clamped out, 32 pk in, 32 out) against ~150 k integer
 // multiply-adds, i.e. the kernel is bound by the integer pipes, not by HBM.
 #include "kernels.h"
@@ -28,14 +28,11 @@ k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, u
     const size_t i = (size_t)blockIdx.x * kLadderThreads + threadIdx.x;
     if (i >= n) return;
     fe k;
-    {   // ecp_TrimSecretKey (curve25519_utils.c:28-32), written back in place like the reference does
-        uint4* q = reinterpret_cast<uint4*>(sk32 + 32 * i);
-        uint4 a = q[0], b = q[1];
-        a.x &= 0xfffffff8u;
-        b.w = (b.w | 0x40000000u) & 0x7fffffffu;
-        q[0] = a; q[1] = b;
-        k.v[0] = a.x; k.v[1] = a.y; k.v[2] = a.z; k.v[3] = a.w; k.v[4] = b.x; k.v[5] = b.y; k.v[6] = b.z; k.v[7] = b.w;
-    }
+    // ecp_TrimSecretKey (curve25519_utils.c:28-32), written back in place like the reference does
+    fe_load_plain(k, sk32 + 32 * i);
+    k.v[0] &= 0xfffffff8u;
+    k.v[7] = (k.v[7] | 0x40000000u) & 0x7fffffffu;
+    fe_store(sk32 + 32 * i, k);
 #pragma unroll
     for (int w = 0; w < 8; w++) ks[w][threadIdx.x] = k.v[w];
     fe u;
