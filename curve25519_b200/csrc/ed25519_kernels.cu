@@ -250,7 +250,8 @@ k_ed25519_verify_init(uint8_t* __restrict__ ctx, const uint8_t* __restrict__ pk3
 #pragma unroll 1
     for (int lvl = 1; lvl < 4; lvl++) {
 #pragma unroll 1
-        for (int d = 0; d < 64; d++) ge_double(Q);              // Q = 2^(64 lvl) (-A)
+        for (int d = 0; d < 63; d++) ge_double<false>(Q);       // T is not an input of a doubling: skip it 63 times
+        ge_double<true>(Q);                                     // Q = 2^(64 lvl) (-A)
         const int base = 1 << lvl;
         ge_to_pe(pe, Q);
         store_pe(tab + 128 * base, pe);

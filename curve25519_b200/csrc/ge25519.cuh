@@ -29,7 +29,11 @@ C25519_DEV void fe_from_const(fe& z, const u32* c)
     for (int i = 0; i < 8; i++) z.v[i] = c[i];
 }
 
-// P <- 2P.   4S + 4M.   Coordinates of P are N on entry and on exit.
+// P <- 2P.   4S + 4M (3M when WITH_T is false).   Coordinates of P are N on entry and on exit.
+// The doubling does not read T, so inside a run of consecutive doublings (the 3 x 64 doublings of the per-key
+// table, ed25519_verify.c:206,212,222) only the last one has to produce it: X, Y, Z -- hence every later
+// point -- are unchanged.
+template <bool WITH_T = true>
 C25519_DEV void ge_double(ge_ext& p)
 {
     fe xx, yy, zz2, s, g, f, e;
@@ -46,7 +50,7 @@ C25519_DEV void ge_double(ge_ext& p)
     fe_mul(p.x, e, f);
     fe_mul(p.y, s, g);
     fe_mul(p.z, g, f);
-    fe_mul(p.t, e, s);
+    if (WITH_T) fe_mul(p.t, e, s);
 }
 
 // shared tail of the two additions: given A, B, C (N) and D = 2 Z1 Z2 (W or N)
