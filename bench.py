@@ -41,6 +41,7 @@ MAC32_PER_OP = {  # algorithmic 32x32->64 multiply-accumulates per operation (SU
     "ed25519_sign": 358 * 72 + 378 * 44,                   # 42 408
     "ed25519_keypair": 358 * 72 + 378 * 44,
     "ed25519_verify": 1884 * 72 + 1529 * 44,               # 202 924
+    "ed25519_verify_check_cached_tables": 994 * 72 + 506 * 44,   # ed25519_Verify_Check only
 }
 HBM_BYTES_PER_OP = {"x25519_shared": 128, "x25519_public": 96, "ed25519_sign": 256, "ed25519_keypair": 128, "ed25519_verify": 164}
 METRIC = "x25519_shared_key_ops_per_sec"
@@ -297,12 +298,21 @@ def main():
         for name, fn in [("x25519_public", lambda: api.x25519_public(d_sk[2], sk_inplace=True, out=d_out[2])),
                          ("ed25519_keypair", lambda: api.ed25519_keypair(seeds)),
                          ("ed25519_sign", lambda: api.ed25519_sign(priv, msgs)),
-                         ("ed25519_verify", lambda: api.ed25519_verify(sig, pub, msgs))]:
+                         ("ed25519_verify", lambda: api.ed25519_verify(sig, pub, msgs)),
+                         ("ed25519_verify_check_cached_tables", None)]:
+            if fn is None:                      # two-phase API: per-key tables built once (ed25519_Verify_Init), many checks
+                nkeys = 4096
+                ctx = api.ed25519_verify_init(pub[:nkeys].contiguous())
+                kidx = (torch.arange(n, device="cuda", dtype=torch.int32) % nkeys).contiguous()
+                priv_k = priv[:nkeys].contiguous()[kidx.long()].contiguous()
+                sig_k = api.ed25519_sign(priv_k, msgs)
+                fn = lambda: api.ed25519_verify_check(ctx, sig_k, msgs, key_index=kidx)
+                assert bool(fn().all())
             sms = time_steps(fn, ssteps, 1, None, torch) / ssteps
             ops = n / (sms * 1e-3)
             secondary[name] = {"value": ops, "unit": "ops/s", "ms_per_step": sms, "msg_bytes": 64 if "ed25519" in name else None,
-                               "mac32_per_op": MAC32_PER_OP[name], "imad_frac": ops * MAC32_PER_OP[name] / peak,
-                               "imad_frac_of_accumulate_form": ops * MAC32_PER_OP[name] / peak_acc}
+                               "mac32_per_op": MAC32_PER_OP.get(name), "imad_frac": ops * MAC32_PER_OP.get(name, 0) / peak,
+                               "imad_frac_of_accumulate_form": ops * MAC32_PER_OP.get(name, 0) / peak_acc}
 
     # ---- BASELINE config 5: mixed batch (1/2 X25519 shared keys, 1/4 Ed25519 sign, 1/4 verify) sharded over the ranks,
     #      results packed into uniform 64-byte records, ONE all-gather per step

@@ -29,6 +29,8 @@ def lib():
         "c25519_launch_count": ([], u64),
         "c25519_x25519_shared_batch": ([vp, vp, vp, sz, vp], i32),
         "c25519_x25519_public_batch": ([vp, vp, sz, i32, vp], i32),
+        "c25519_x25519_scalarmult_raw_batch": ([vp, vp, vp, sz, vp], i32),
+        "c25519_x25519_scalarmult_raw_host": ([vp, vp, vp, sz], i32),
         "c25519_x25519_shared_host": ([vp, vp, vp, sz], i32),
         "c25519_x25519_public_host": ([vp, vp, sz, i32], i32),
         "c25519_ed25519_keypair_batch": ([vp, vp, vp, sz, vp], i32),
@@ -43,6 +45,7 @@ def lib():
         "c25519_imad_peak_kernel": ([C.POINTER(u64), vp, i32, vp], i32),
         # the reference's 11-function API (include/c25519_legacy.h)
         "ecp_TrimSecretKey": ([vp], None),
+        "ecp_PointMultiply": ([vp, vp, vp, i32], None),
         "curve25519_dh_CalculatePublicKey": ([vp, vp], None),
         "curve25519_dh_CalculatePublicKey_fast": ([vp, vp], None),
         "curve25519_dh_CreateSharedKey": ([vp, vp, vp], None),

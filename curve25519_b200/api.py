@@ -79,6 +79,20 @@ def x25519_shared(pk, sk, out=None, sk_inplace=False):
     return out, skc
 
 
+def x25519_scalarmult_raw(point, scalar):
+    """ecp_PointMultiply (curve25519_dh.c:94) over a batch: k*P for ANY 256-bit scalar, no clamping."""
+    L = lib()
+    if _is_dev(point):
+        point = _tt(point, 32); scalar = _tt(scalar, 32)
+        out = torch.empty_like(point)
+        check(L.c25519_x25519_scalarmult_raw_batch(_p(out), _p(point), _p(scalar), point.shape[0], _stream()), "x25519_scalarmult_raw_batch")
+        return out
+    point = _np(point, 32); scalar = _np(scalar, 32)
+    out = np.empty_like(point)
+    check(L.c25519_x25519_scalarmult_raw_host(_p(out), _p(point), _p(scalar), point.shape[0]), "x25519_scalarmult_raw_host")
+    return out
+
+
 def x25519_public(sk, ladder=False, out=None, sk_inplace=False):
     """curve25519_dh_CalculatePublicKey_fast (dh.c:182, ladder=False: 8-fold comb) or
     curve25519_dh_CalculatePublicKey (dh.c:192, ladder=True) over a batch -> (pk[n,32], clamped_sk)."""

@@ -191,6 +191,15 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
     return 0;
 }
 
+int c25519_x25519_scalarmult_raw_batch(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, void* stream)
+{
+    if (int rc = check_ready()) return rc;
+    if (n && (!out32 || !point32 || !scalar32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(out32) || misaligned32(point32) || misaligned32(scalar32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    CK(launch_x25519_ladder_raw(out32, point32, scalar32, n, (cudaStream_t)stream));
+    return 0;
+}
+
 int c25519_x25519_public_batch(uint8_t* pk32, uint8_t* sk32_inout, size_t n, int ladder, void* stream)
 {
     if (int rc = check_ready()) return rc;
@@ -269,6 +278,13 @@ int c25519_x25519_shared_host(uint8_t* out32, const uint8_t* pk32, uint8_t* sk32
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     Field f[3] = {{32, false, true, nullptr, out32}, {32, true, false, pk32, nullptr}, {32, true, true, sk32_inout, sk32_inout}};
     return run_host_pipeline(f, n, [](uint8_t** d, size_t cnt, cudaStream_t s) { return launch_x25519_ladder(d[0], d[1], d[2], cnt, s); });
+}
+
+int c25519_x25519_scalarmult_raw_host(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n)
+{
+    if (n && (!out32 || !point32 || !scalar32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    Field f[3] = {{32, false, true, nullptr, out32}, {32, true, false, point32, nullptr}, {32, true, false, scalar32, nullptr}};
+    return run_host_pipeline(f, n, [](uint8_t** d, size_t cnt, cudaStream_t s) { return launch_x25519_ladder_raw(d[0], d[1], d[2], cnt, s); });
 }
 
 int c25519_x25519_public_host(uint8_t* pk32, uint8_t* sk32_inout, size_t n, int ladder)
@@ -364,6 +380,16 @@ static void die_if(int rc, const char* fn)
 
 // RFC 7748 clamp on a caller's host buffer (curve25519_utils.c:28-32); the batch kernels clamp on the device
 void ecp_TrimSecretKey(unsigned char* sk) { sk[0] &= 0xf8; sk[31] = (unsigned char)((sk[31] | 0x40) & 0x7f); }
+
+// Generic k*P exported by the reference's library (source/curve25519_mehdi.h:93) and used by its self-test:
+// K is `len` little-endian bytes (len <= 32), not clamped, not modified.
+void ecp_PointMultiply(unsigned char* Q, const unsigned char* P, const unsigned char* K, int len)
+{
+    unsigned char k[32] = {0};
+    if (len > 32) len = 32;
+    if (len > 0) memcpy(k, K, (size_t)len);
+    die_if(c25519_x25519_scalarmult_raw_host(Q, P, k, 1), "ecp_PointMultiply");
+}
 
 void curve25519_dh_CalculatePublicKey(unsigned char* pk, unsigned char* sk)
 { die_if(c25519_x25519_public_host(pk, sk, 1, 1), "curve25519_dh_CalculatePublicKey"); }

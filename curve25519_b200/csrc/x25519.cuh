@@ -77,6 +77,33 @@ C25519_DEV void x25519_ladder_projective(fe& PX, fe& PZ, const fe& u, KeyWord kw
     fe_select(PZ, R1Z, R0Z, cur);
 }
 
+// Generic k*P for ANY 256-bit scalar (no clamping): ecp_PointMultiply's general contract (curve25519_dh.c:94-157:
+// "MSB-first from the top set bit; K = 0 gives 32 zero bytes").  Instead of searching for the top set bit -- which
+// would make lanes diverge -- the ladder starts one level higher, at (P, Q) = (O, (u:1)) with O = (1:0), and walks
+// all 256 bits: leading zero bits map O to O (doubling) and (u:1) to itself up to a projective factor (differential
+// addition with O), so when the top set bit arrives the state equals the reference's start (P, Q) = ((u:1), 2(u:1))
+// projectively, and K = 0 ends with Z = 0, i.e. zeros.  Two ladder steps dearer than the clamped fast path.
+template <typename KeyWord>
+C25519_DEV void x25519_ladder_projective_raw(fe& PX, fe& PZ, const fe& u, KeyWord kw)
+{
+    fe R0X, R0Z, R1X, R1Z;
+    fe_set_u32(R0X, 1); fe_set_u32(R0Z, 0);          // P = O
+    fe_set_u32(R1Z, 1);
+    { fe one; fe_set_u32(one, 1); fe_mul(R1X, u, one); }   // Q = (u : 1), narrow representative
+    bool cur = true;
+#pragma unroll 1
+    for (int bit = 255; bit >= 0; --bit) {
+        bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
+        bool s = (b != cur);
+        fe_cswap(R0X, R1X, s);
+        fe_cswap(R0Z, R1Z, s);
+        cur = b;
+        mont_step(R0X, R0Z, R1X, R1Z, u);
+    }
+    fe_select(PX, R1X, R0X, cur);
+    fe_select(PZ, R1Z, R0Z, cur);
+}
+
 // out = canonical x-coordinate of [k]u (single-operation form: own inversion).
 template <typename KeyWord>
 C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)

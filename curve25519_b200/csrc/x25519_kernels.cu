@@ -51,6 +51,40 @@ k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, u
     }
 }
 
+// Generic scalar multiplication, no clamping, scalar NOT modified (ecp_PointMultiply, curve25519_dh.c:94).
+__global__ void __launch_bounds__(kLadderThreads)
+k_x25519_ladder_raw(const uint8_t* __restrict__ pk32, const uint8_t* __restrict__ k32, size_t n, uint8_t* __restrict__ scratch)
+{
+    __shared__ u32 ks[8][kLadderThreads];
+    const size_t i = (size_t)blockIdx.x * kLadderThreads + threadIdx.x;
+    if (i >= n) return;
+    fe k, u;
+    fe_load(k, k32 + 32 * i);
+#pragma unroll
+    for (int w = 0; w < 8; w++) ks[w][threadIdx.x] = k.v[w];
+    fe_load(u, pk32 + 32 * i);
+    const int t = threadIdx.x;
+    fe PX, PZ;
+    x25519_ladder_projective_raw(PX, PZ, u, [&](int w) { return ks[w][t]; });
+    fe_store(scratch + kScratchXZ * i, PX);
+    fe_store(scratch + kScratchXZ * i + 32, PZ);
+}
+
+cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, n * kScratchXZ, s);
+    if (e != cudaSuccess) return e;
+    k_x25519_ladder_raw<<<grid, kLadderThreads, 0, s>>>(point32, scalar32, n, scratch);
+    count_launch();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s);
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
+}
+
 // ---- batched normalisation kernel (shared by every operation of the path) ---------------------------
 template <int MODE>
 __global__ void __launch_bounds__(128)

@@ -28,6 +28,9 @@ extern "C" {
 /* Host-side key clamp exported by the reference's library and used by its own test program
  * (source/curve25519_utils.c:28-32, declared in source/curve25519_mehdi.h:96): two byte masks, no curve work. */
 void ecp_TrimSecretKey(unsigned char *sk);
+/* Generic scalar multiplication exported by the reference's library (source/curve25519_mehdi.h:93): Q = K * P on the
+ * Montgomery x-line, K = `len` little-endian bytes (len <= 32), NOT clamped, not modified; K = 0 gives 32 zero bytes. */
+void ecp_PointMultiply(unsigned char *Q, const unsigned char *P, const unsigned char *K, int len);
 
 void curve25519_dh_CalculatePublicKey(unsigned char *pk, unsigned char *sk);
 void curve25519_dh_CalculatePublicKey_fast(unsigned char *pk, unsigned char *sk);

@@ -134,3 +134,38 @@ def test_full_size_1m_properties(engine, oracle, rng):
     s3, _ = engine.x25519_shared(_dev(pk), da)
     exp, _ = oracle.x25519_shared(pk[idx], sk_a[idx], threads=os.cpu_count() or 1)
     assert (s3.cpu().numpy()[idx] == exp).all()
+
+
+def test_generic_scalarmult_unclamped(engine, oracles, rng):
+    """ecp_PointMultiply (curve25519_dh.c:94-157) with ARBITRARY scalars: no clamping, leading zero bits, K = 0 -> zeros,
+    bit 255 of K honoured -- against the checkers' own ecp_PointMultiply, record by record; plus the reference
+    self-test's group-order identities through the ladder ((L-1) B and (L+1) B share B's u-coordinate, L B -> zeros;
+    test/curve25519_selftest.c:752-767)."""
+    n = 600
+    k = rng.integers(0, 256, (n, 32), dtype=np.uint8); u = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    L = V.L_ORDER
+    specials = [0, 1, 2, 3, 8, L - 1, L, L + 1, 2 * L, 2**255 - 19, 2**255, 2**256 - 1, 2**254, 1 << 200, 0x8000000000000000]
+    for i, s in enumerate(specials):
+        k[i] = np.frombuffer(s.to_bytes(32, "little"), np.uint8)
+    for i, h in enumerate(V.X25519_LOW_ORDER_U):
+        u[40 + i] = hx(h)
+    u[:20] = hx("09" + "00" * 31)
+    out = engine.x25519_scalarmult_raw(_dev(u), _dev(k)).cpu().numpy()
+    out_h = engine.x25519_scalarmult_raw(u, k)
+    assert (out == out_h).all()
+    for name, o in oracles.items():
+        buf = (C.c_uint8 * 32)()
+        for i in range(n):
+            o.lib.ecp_PointMultiply(buf, u[i].ctypes.data_as(C.c_void_p), k[i].ctypes.data_as(C.c_void_p), 32)
+            assert bytes(buf) == out[i].tobytes(), (name, i, k[i].tobytes().hex(), u[i].tobytes().hex())
+    nine = "09" + "00" * 31
+    assert out[5].tobytes().hex() == nine and out[7].tobytes().hex() == nine      # (L-1) B, (L+1) B
+    assert not out[0].any() and not out[6].any() and not out[8].any()             # 0 B, L B, 2L B
+    # the legacy symbol, with a short scalar (len < 32)
+    from curve25519_b200 import _native
+    q = (C.c_uint8 * 32)(); kk = (C.c_uint8 * 2)(0x39, 0x05)
+    _native.lib().ecp_PointMultiply(q, u[0].ctypes.data_as(C.c_void_p), kk, 2)
+    for name, o in oracles.items():
+        buf = (C.c_uint8 * 32)()
+        o.lib.ecp_PointMultiply(buf, u[0].ctypes.data_as(C.c_void_p), kk, 2)
+        assert bytes(buf) == bytes(q), name
