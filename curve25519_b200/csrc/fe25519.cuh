@@ -87,6 +87,24 @@ C25519_DEV void fold9(u32* z, u32 w8)
 C25519_DEV void reduce16(fe& z, u32* t)
 {
     u32 u[8], w8;
+#ifdef C25519_FRESH_FOLD
+    {   // EXPERIMENT: all eight x38 products with a zero accumulator, merged by one more add chain
+        u32 e[8];
+        mul_wide(e[0], e[1], t[8], 38u); mul_wide(e[2], e[3], t[10], 38u);
+        mul_wide(e[4], e[5], t[12], 38u); mul_wide(e[6], e[7], t[14], 38u);
+        asm("add.cc.u32  %0, %0, %9;\n\t"
+            "addc.cc.u32 %1, %1, %10;\n\t"
+            "addc.cc.u32 %2, %2, %11;\n\t"
+            "addc.cc.u32 %3, %3, %12;\n\t"
+            "addc.cc.u32 %4, %4, %13;\n\t"
+            "addc.cc.u32 %5, %5, %14;\n\t"
+            "addc.cc.u32 %6, %6, %15;\n\t"
+            "addc.cc.u32 %7, %7, %16;\n\t"
+            "addc.u32 %8, 0, 0;"
+            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "=&r"(w8)
+            : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]));
+    }
+#else
     // even columns of 38*T_hi accumulate straight into T_lo (carry chain); odd columns are fresh
     asm("{\n\t"
         "mad.lo.cc.u32  %0, %9, %17, %0;\n\t"
@@ -101,6 +119,7 @@ C25519_DEV void reduce16(fe& z, u32* t)
         "}"
         : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "=&r"(w8)
         : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(38u));
+#endif
     mul_wide(u[0], u[1], t[9], 38u);
     mul_wide(u[2], u[3], t[11], 38u);
     mul_wide(u[4], u[5], t[13], 38u);
@@ -363,6 +382,21 @@ C25519_DEV void fe_sqr(fe& z, const fe& x)
         "addc.u32    %14, %14, %14;"
         : "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]), "+r"(A[8]),
           "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15]));
+#ifdef C25519_FRESH_DIAG
+    {   // EXPERIMENT: diagonal squares with a zero accumulator + one 16-word add chain
+        u32 d[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) mul_wide(d[2 * i], d[2 * i + 1], a[i], a[i]);
+        asm("add.cc.u32  %0, %0, %16;\n\t"  "addc.cc.u32 %1, %1, %17;\n\t"  "addc.cc.u32 %2, %2, %18;\n\t"  "addc.cc.u32 %3, %3, %19;\n\t"
+            "addc.cc.u32 %4, %4, %20;\n\t"  "addc.cc.u32 %5, %5, %21;\n\t"  "addc.cc.u32 %6, %6, %22;\n\t"  "addc.cc.u32 %7, %7, %23;\n\t"
+            "addc.cc.u32 %8, %8, %24;\n\t"  "addc.cc.u32 %9, %9, %25;\n\t"  "addc.cc.u32 %10, %10, %26;\n\t" "addc.cc.u32 %11, %11, %27;\n\t"
+            "addc.cc.u32 %12, %12, %28;\n\t" "addc.cc.u32 %13, %13, %29;\n\t" "addc.cc.u32 %14, %14, %30;\n\t" "addc.u32 %15, %15, %31;"
+            : "+r"(A[0]), "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]),
+              "+r"(A[8]), "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15])
+            : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]),
+              "r"(d[8]), "r"(d[9]), "r"(d[10]), "r"(d[11]), "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15]));
+    }
+#else
     // T += sum x_i^2 * 2^(64 i)
     asm("{\n\t"
         "mad.lo.cc.u32  %0, %16, %16, %0;\n\t"   "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
@@ -377,6 +411,7 @@ C25519_DEV void fe_sqr(fe& z, const fe& x)
         : "+r"(A[0]), "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]),
           "+r"(A[8]), "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#endif
     reduce16(z, A);
 }
 

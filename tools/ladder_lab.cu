@@ -82,5 +82,6 @@ int main(int argc,char**argv){
     timeit("T128 min6 (<=80 regs)",  k_ladder<128,6>,128,c.n,c,false);
     timeit("T64  min8",              k_ladder<64,8>,64,c.n,c,false);
     timeit("T256 min2",              k_ladder<256,2>,256,c.n,c,false);
+    { unsigned long long hsh=1469598103934665603ull; for(size_t i=0;i<c.href.size();i++){ hsh^=c.href[i]; hsh*=1099511628211ull; } printf("output fnv1a64 = %016llx\n", hsh); }
     return 0;
 }
