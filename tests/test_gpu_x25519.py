@@ -125,15 +125,18 @@ def test_full_size_1m_properties(engine, oracle, rng):
     assert torch.equal(ca, ca2)
     exp_sk = sk_a.copy(); exp_sk[:, 0] &= 0xF8; exp_sk[:, 31] = (exp_sk[:, 31] | 0x40) & 0x7F
     assert (ca.cpu().numpy() == exp_sk).all()
-    idx = rng.choice(n, 4096, replace=False)
+    # SURVEY 8d config 2 asks for 100 % byte equality on the whole batch: with >= 32 host cores the oracle does all
+    # 2^20 records in seconds; on smaller hosts a random 4096-record sample is checked instead.
+    ncpu = os.cpu_count() or 1
+    idx = np.arange(n) if ncpu >= 32 else rng.choice(n, 4096, replace=False)
     pb_h = pb.cpu().numpy()
-    exp, _ = oracle.x25519_shared(pb_h[idx], sk_a[idx], threads=os.cpu_count() or 1)
+    exp, _ = oracle.x25519_shared(pb_h[idx], sk_a[idx], threads=ncpu)
     assert (s1.cpu().numpy()[idx] == exp).all()
-    # and uniformly random (mostly off-curve / twist, bit 255 set in half) peer points at full size, sampled
+    # and uniformly random (mostly off-curve / twist, bit 255 set in half) peer points at full size
     pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
-    s3, _ = engine.x25519_shared(_dev(pk), da)
-    exp, _ = oracle.x25519_shared(pk[idx], sk_a[idx], threads=os.cpu_count() or 1)
-    assert (s3.cpu().numpy()[idx] == exp).all()
+    s3, c3 = engine.x25519_shared(_dev(pk), da)
+    exp, exp_sk = oracle.x25519_shared(pk[idx], sk_a[idx], threads=ncpu)
+    assert (s3.cpu().numpy()[idx] == exp).all() and (c3.cpu().numpy()[idx] == exp_sk).all()
 
 
 def test_generic_scalarmult_unclamped(engine, oracles, rng):
