@@ -79,6 +79,14 @@ def x25519_shared(pk, sk, out=None, sk_inplace=False):
     return out, skc
 
 
+def x25519_shared_kdf(pk, sk, key_size=32):
+    """X25519Private::CreateSharedKey (C++/x25519.cpp:75-95): SHA-512(shared secret)[:key_size] per record (device tensors)."""
+    pk = _tt(pk, 32); skc = _tt(sk, 32).clone()
+    out = torch.empty((skc.shape[0], key_size), dtype=torch.uint8, device=skc.device)
+    check(lib().c25519_x25519_shared_kdf_batch(_p(out), key_size, _p(pk), _p(skc), skc.shape[0], _stream()), "x25519_shared_kdf_batch")
+    return out
+
+
 def x25519_scalarmult_raw(point, scalar):
     """ecp_PointMultiply (curve25519_dh.c:94) over a batch: k*P for ANY 256-bit scalar, no clamping."""
     L = lib()

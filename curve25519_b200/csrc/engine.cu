@@ -110,7 +110,11 @@ int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
     if (int rc = ensure_init_locked()) return rc;
     CK(cudaSetDevice(g_device));
     if (n == 0) return 0;
-    const size_t chunk = std::min(n, kChunkOps);
+    size_t rec_total = 0;
+    for (int k = 0; k < NF; k++) rec_total += f[k].rec;
+    // slice size: 2^17 operations, fewer when records are large (long messages) so a stage stays <= 256 MB
+    const size_t by_bytes = std::max<size_t>(1, ((size_t)256 << 20) / rec_total);
+    const size_t chunk = std::min(n, std::min(kChunkOps, by_bytes));
     size_t offs[NF + 1]; offs[0] = 0;
     for (int k = 0; k < NF; k++) offs[k + 1] = offs[k] + align_up(f[k].rec * chunk, 256);
     for (auto& st : g_stage) if (int rc = reserve(st, offs[NF])) return rc;
@@ -188,6 +192,16 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(out32) || misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     CK(launch_x25519_ladder(out32, pk32, sk32_inout, n, (cudaStream_t)stream));
+    return 0;
+}
+
+int c25519_x25519_shared_kdf_batch(uint8_t* key_out, size_t key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, void* stream)
+{
+    if (int rc = check_ready()) return rc;
+    if (n && (!key_out || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (key_size == 0 || key_size > 64) return fail(C25519_E_BAD_ARGUMENT, "key_size must be 1..64 (bytes of the SHA-512 digest)");
+    if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    CK(launch_x25519_shared_kdf(key_out, (unsigned)key_size, pk32, sk32_inout, n, (cudaStream_t)stream));
     return 0;
 }
 

@@ -32,7 +32,8 @@ k_test_fe(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, cons
     fe_store(out + 32 * i, z);
 }
 
-// op 8: (a || b) as a 512-bit little-endian integer mod L -> 32 bytes;  op 9: SHA-512(a || b) -> 64 bytes
+// op 8: (a || b) as a 512-bit little-endian integer mod L -> 32 bytes;  op 9: SHA-512(a || b) -> 64 bytes;
+// op 11: (a*b + a) mod L -> 32 bytes
 __global__ void __launch_bounds__(128)
 k_test_sc_sha(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n)
 {
@@ -40,7 +41,14 @@ k_test_sc_sha(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, 
     if (i >= n) return;
     fe x, y;
     fe_load(x, a + 32 * i); fe_load(y, b + 32 * i);
-    if (op == 8) {
+    if (op == 11) {            // (a*b + a) mod L through sc_muladd (eco_MulReduce + eco_AddReduce + eco_Mod)
+        u32 r[8];
+        sc_muladd(r, x.v, y.v, x.v);
+        fe z;
+#pragma unroll
+        for (int k = 0; k < 8; k++) z.v[k] = r[k];
+        fe_store(out + 32 * i, z);
+    } else if (op == 8) {
         u32 w[16], r[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { w[k] = x.v[k]; w[8 + k] = y.v[k]; }
@@ -65,7 +73,7 @@ cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const 
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (op == 8 || op == 9) k_test_sc_sha<<<grid, 128, 0, s>>>(op, out, a, b, n);
+    if (op == 8 || op == 9 || op == 11) k_test_sc_sha<<<grid, 128, 0, s>>>(op, out, a, b, n);
     else k_test_fe<<<grid, 128, 0, s>>>(op, out, a, b, n);
     count_launch();
     return cudaGetLastError();

@@ -10,6 +10,7 @@
 // multiply-adds, i.e. the kernel is bound by the integer pipes, not by HBM.
 #include "kernels.h"
 #include "normalize.cuh"
+#include "sha512.cuh"
 #include "x25519.cuh"
 
 namespace c25519 {
@@ -82,6 +83,38 @@ cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, con
     e = cudaGetLastError();
     if (e == cudaSuccess) e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s);
     cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
+}
+
+// Shared KEY = first key_size bytes of SHA-512(shared secret): what the reference's C++ wrapper derives
+// (X25519Private::CreateSharedKey, C++/x25519.cpp:75-95).  One 32-byte secret per thread, one compression.
+__global__ void __launch_bounds__(128)
+k_x25519_kdf_sha512(uint8_t* __restrict__ key_out, unsigned key_size, const uint8_t* __restrict__ secret32, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    fe sct; fe_load_plain(sct, secret32 + 32 * i);
+    u64 pre[4], dg[8]; u32 w[16];
+    le_limbs_to_be64(pre, sct.v);
+    sha512_prefixed<4>(dg, pre, nullptr, 0);
+    sha512_digest_to_le_words(w, dg);
+    uint8_t* o = key_out + (size_t)key_size * i;
+    for (unsigned b = 0; b < key_size; b++) o[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+}
+
+cudaError_t launch_x25519_shared_kdf(uint8_t* key_out, unsigned key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    uint8_t* secret = nullptr;
+    cudaError_t e = cudaMallocAsync(&secret, n * 32, s);
+    if (e != cudaSuccess) return e;
+    e = launch_x25519_ladder(secret, pk32, sk32_inout, n, s);
+    if (e == cudaSuccess) {
+        k_x25519_kdf_sha512<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(key_out, key_size, secret, n);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaFreeAsync(secret, s);
     return e != cudaSuccess ? e : e2;
 }
 

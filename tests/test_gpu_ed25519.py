@@ -227,3 +227,16 @@ def test_full_size_1m_round_trip(engine, oracle, rng):
     assert (sig.cpu().numpy()[idx] == exp_sig).all()
     exp_ok = oracle.ed25519_verify(bad.cpu().numpy()[idx], exp_pub, msgs[idx], threads=NCPU)
     assert (ok.cpu().numpy()[idx] == exp_ok).all()
+
+
+def test_device_sc_muladd(engine, rng):
+    """op 11: (a*b + a) mod L through sc_muladd, incl. operands >= L and all-ones."""
+    n = 2048
+    a = rng.integers(0, 256, (n, 32), dtype=np.uint8); b = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    a[0] = 255; b[0] = 255; a[1] = 0; b[2] = 0
+    for j, v in enumerate([V.L_ORDER, V.L_ORDER - 1, V.L_ORDER + 1, 15 * V.L_ORDER, 2**252, 2**256 - 1]):
+        a[10 + j] = np.frombuffer(v.to_bytes(32, "little"), np.uint8); b[20 + j] = a[10 + j]
+    got = engine.test_primitive(11, _dev(a), _dev(b)).cpu().numpy()
+    for i in range(n):
+        x = int.from_bytes(a[i].tobytes(), "little"); y = int.from_bytes(b[i].tobytes(), "little")
+        assert int.from_bytes(got[i].tobytes(), "little") == (x * y + x) % V.L_ORDER, i

@@ -172,3 +172,15 @@ def test_generic_scalarmult_unclamped(engine, oracles, rng):
         buf = (C.c_uint8 * 32)()
         o.lib.ecp_PointMultiply(buf, u[0].ctypes.data_as(C.c_void_p), kk, 2)
         assert bytes(buf) == bytes(q), name
+
+
+@pytest.mark.parametrize("key_size", [1, 16, 32, 48, 64])
+def test_shared_key_kdf_matches_cxx_wrapper(engine, oracle, rng, key_size):
+    """X25519Private::CreateSharedKey (C++/x25519.cpp:75-95): SHA-512 of the shared secret, truncated."""
+    import hashlib
+    n = 700
+    sk = rng.integers(0, 256, (n, 32), dtype=np.uint8); pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    secret, _ = oracle.x25519_shared(pk, sk, threads=os.cpu_count() or 1)
+    got = engine.x25519_shared_kdf(_dev(pk), _dev(sk), key_size).cpu().numpy()
+    for i in range(n):
+        assert got[i].tobytes() == hashlib.sha512(secret[i].tobytes()).digest()[:key_size], i
