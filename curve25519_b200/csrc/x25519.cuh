@@ -64,7 +64,11 @@ C25519_DEV void x25519_ladder_projective(fe& PX, fe& PZ, const fe& u, KeyWord kw
     // make R0X narrow: u is an arbitrary 256-bit value, the step wants N inputs for its lazy additions
     { fe one; fe_set_u32(one, 1); fe_mul(R0X, R0X, one); }
     bool cur = true;
-#pragma unroll 1
+#ifndef C25519_LADDER_UNROLL
+#define C25519_LADDER_UNROLL 1
+#endif
+    constexpr int kLadderUnroll = C25519_LADDER_UNROLL;     // > 1 was measured: no gain (profiles/), code size doubles
+#pragma unroll kLadderUnroll
     for (int bit = 253; bit >= 0; --bit) {
         bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
         bool s = (b != cur);
