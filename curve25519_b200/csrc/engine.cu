@@ -29,6 +29,7 @@ namespace {
 std::mutex g_mu;                       // guards init/shutdown and the host-pointer pipeline
 bool g_ready = false;
 int g_device = -1;
+int g_requested_device = -1;           // set by c25519_init(); -1 = take $C25519_DEVICE, default 0
 std::atomic<uint64_t> g_launches{0};
 thread_local char t_err[256] = "";
 
@@ -57,7 +58,8 @@ int ensure_init_locked()
 {
     if (g_ready) return 0;
     int dev = 0;
-    if (const char* e = getenv("C25519_DEVICE")) dev = atoi(e);
+    if (g_requested_device >= 0) dev = g_requested_device;
+    else if (const char* e = getenv("C25519_DEVICE")) dev = atoi(e);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return fail(C25519_E_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)");
@@ -161,7 +163,8 @@ int c25519_init(int device)
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ready && device == g_device) return 0;
     if (g_ready) return fail(C25519_E_BAD_ARGUMENT, "already initialised on another device; call c25519_shutdown first");
-    char buf[16]; snprintf(buf, sizeof buf, "%d", device); setenv("C25519_DEVICE", buf, 1);
+    if (device < 0) return fail(C25519_E_BAD_ARGUMENT, "device ordinal must be >= 0");
+    g_requested_device = device;
     return ensure_init_locked();
 }
 
@@ -179,6 +182,7 @@ int c25519_shutdown(void)
     cudaFree(const_cast<uint32_t*>(g_comb_table_dev));
     g_comb_table_dev = nullptr;
     g_ready = false;
+    g_requested_device = -1;
     return 0;
 }
 
