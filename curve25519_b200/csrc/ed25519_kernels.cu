@@ -237,8 +237,7 @@ k_ed25519_verify_init(uint8_t* __restrict__ ctx, const uint8_t* __restrict__ pk3
         ge_recover_x(Q.x, Q.y, sign ^ 1u);
         fe_mul(Q.t, Q.x, Q.y);
         fe_set_u32(Q.z, 1);
-        fe one; fe_set_u32(one, 1);
-        fe_mul(Q.x, Q.x, one); fe_mul(Q.y, Q.y, one);          // narrow representatives for the lazy adds
+        fe_narrow(Q.x); fe_narrow(Q.y);                         // narrow representatives for the lazy adds
     }
     {   // entry 0 = neutral element (1, 1, 0, 2)                                            (:201-204)
         ge_pe id; fe_set_u32(id.ypx, 1); fe_set_u32(id.ymx, 1); fe_set_u32(id.t2d, 0); fe_set_u32(id.z2, 2);

@@ -563,6 +563,9 @@ C25519_DEV void fe_canon(fe& z)
     for (int i = 0; i < 8; i++) z.v[i] = ge ? s[i] : t[i];
 }
 
+// z <- the same field element with a narrow representative (< 2^255 + 19): one fold at bit 255, no multiplication.
+C25519_DEV void fe_narrow(fe& z) { fold9(z.v, 0); }
+
 C25519_DEV void fe_set_u32(fe& z, u32 v)
 { z.v[0] = v;
 #pragma unroll

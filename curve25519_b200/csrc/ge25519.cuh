@@ -112,8 +112,7 @@ C25519_DEV void ge_from_pe(ge_ext& s, const ge_pe& q)
     fe_mul(s.t, q.t2d, di);
     fe_copy(s.z, q.z2);
     // make x, y, z narrow for the lazy additions downstream
-    fe one; fe_set_u32(one, 1);
-    fe_mul(s.x, s.x, one); fe_mul(s.y, s.y, one); fe_mul(s.z, s.z, one);
+    fe_narrow(s.x); fe_narrow(s.y); fe_narrow(s.z);
 }
 
 // comb indices ------------------------------------------------------------------------------------
@@ -169,8 +168,7 @@ C25519_DEV void ge_base_comb(ge_ext& S, const u32 (&a)[8], const u32* __restrict
         fe_add_nn(S.y, q.ypx, q.ymx);       // 2y
         fe_mul(S.t, q.t2d, di);             // 2xy
         fe_set_u32(S.z, 2);
-        fe one; fe_set_u32(one, 1);
-        fe_mul(S.x, S.x, one); fe_mul(S.y, S.y, one);      // narrow
+        fe_narrow(S.x); fe_narrow(S.y);
     }
 #pragma unroll 1
     for (int i = 1; i < 32; i++) {

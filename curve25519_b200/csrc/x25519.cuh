@@ -62,7 +62,7 @@ C25519_DEV void x25519_ladder_projective(fe& PX, fe& PZ, const fe& u, KeyWord kw
     fe_set_u32(R0Z, 1);
     mont_double(R1X, R1Z, R0X, R0Z);
     // make R0X narrow: u is an arbitrary 256-bit value, the step wants N inputs for its lazy additions
-    { fe one; fe_set_u32(one, 1); fe_mul(R0X, R0X, one); }
+    fe_narrow(R0X);
     bool cur = true;
 #ifndef C25519_LADDER_UNROLL
 #define C25519_LADDER_UNROLL 1
@@ -93,7 +93,7 @@ C25519_DEV void x25519_ladder_projective_raw(fe& PX, fe& PZ, const fe& u, KeyWor
     fe R0X, R0Z, R1X, R1Z;
     fe_set_u32(R0X, 1); fe_set_u32(R0Z, 0);          // P = O
     fe_set_u32(R1Z, 1);
-    { fe one; fe_set_u32(one, 1); fe_mul(R1X, u, one); }   // Q = (u : 1), narrow representative
+    fe_copy(R1X, u); fe_narrow(R1X);                  // Q = (u : 1), narrow representative
     bool cur = true;
 #pragma unroll 1
     for (int bit = 255; bit >= 0; --bit) {
