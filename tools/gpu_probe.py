@@ -5,7 +5,7 @@ import numpy as np, torch
 from curve25519_b200 import api
 api.init(0)
 peak = api.imad_peak()
-print("imad_peak MAC32/s = %.4e" % peak)
+print("imad_peak (fresh form) MAC32/s = %.4e" % peak)
 rng = np.random.Generator(np.random.PCG64(1))
 res = {}
 for n in (1 << 16, 1 << 18, 1 << 20, 1 << 22):
