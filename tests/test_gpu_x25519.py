@@ -184,3 +184,24 @@ def test_shared_key_kdf_matches_cxx_wrapper(engine, oracle, rng, key_size):
     got = engine.x25519_shared_kdf(_dev(pk), _dev(sk), key_size).cpu().numpy()
     for i in range(n):
         assert got[i].tobytes() == hashlib.sha512(secret[i].tobytes()).digest()[:key_size], i
+
+
+def test_abi_argument_checks(engine):
+    """Error behaviour of the batched ABI: misaligned device record arrays, null pointers and bad key sizes are refused
+    with C25519_E_BAD_ARGUMENT (-3) and a message; nothing is launched."""
+    import torch
+    from curve25519_b200 import _native
+    L = _native.lib()
+    buf = torch.zeros(4 * 32 + 64, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr()
+    base += (-base) % 32
+    before = L.c25519_launch_count()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.c25519_x25519_shared_batch(C.c_void_p(base + 1), C.c_void_p(base + 32), C.c_void_p(base + 64), 1, s) == -3
+    assert b"aligned" in L.c25519_last_error()
+    assert L.c25519_x25519_shared_batch(None, C.c_void_p(base + 32), C.c_void_p(base + 64), 1, s) == -3
+    assert L.c25519_x25519_shared_kdf_batch(C.c_void_p(base), 0, C.c_void_p(base + 32), C.c_void_p(base + 64), 1, s) == -3
+    assert L.c25519_x25519_shared_kdf_batch(C.c_void_p(base), 65, C.c_void_p(base + 32), C.c_void_p(base + 64), 1, s) == -3
+    assert L.c25519_launch_count() == before
+    # n = 0 is a no-op that succeeds even with null pointers
+    assert L.c25519_x25519_shared_batch(None, None, None, 0, s) == 0
