@@ -4,6 +4,7 @@
 // IMAD.WIDE roofline denominator on the very device it is timing.
 #include "kernels.h"
 #include "fe25519.cuh"
+#include "ge25519.cuh"
 #include "sc25519.cuh"
 #include "sha512.cuh"
 
@@ -40,8 +41,13 @@ k_test_sc_sha(int op, uint8_t* __restrict__ out, const uint8_t* __restrict__ a, 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe x, y;
-    fe_load(x, a + 32 * i); fe_load(y, b + 32 * i);
-    if (op == 11) {            // (a*b + a) mod L through sc_muladd (eco_MulReduce + eco_AddReduce + eco_Mod)
+    fe_load(x, a + 32 * i);
+    if (b) fe_load(y, b + 32 * i); else fe_set_u32(y, 0);
+    if (op == 12 || op == 13) { // comb index extraction: ecp_8Folds (32 bytes out) / ecp_4Folds (64 bytes out) of a
+        const int cnt = op == 12 ? 32 : 64;
+        uint8_t* o = out + (size_t)cnt * i;
+        for (int j = 0; j < cnt; j++) o[j] = (uint8_t)(op == 12 ? comb8_index(x.v, j) : comb4_index(x.v, j));
+    } else if (op == 11) {     // (a*b + a) mod L through sc_muladd (eco_MulReduce + eco_AddReduce + eco_Mod)
         u32 r[8];
         sc_muladd(r, x.v, y.v, x.v);
         fe z;
@@ -73,7 +79,7 @@ cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const 
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    if (op == 8 || op == 9 || op == 11) k_test_sc_sha<<<grid, 128, 0, s>>>(op, out, a, b, n);
+    if (op == 8 || op == 9 || op >= 11) k_test_sc_sha<<<grid, 128, 0, s>>>(op, out, a, b, n);
     else k_test_fe<<<grid, 128, 0, s>>>(op, out, a, b, n);
     count_launch();
     return cudaGetLastError();

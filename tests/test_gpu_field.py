@@ -72,3 +72,21 @@ def test_field_mul_vs_oracle_primitive(engine, oracles, rng):
             R.ecp_MulReduce(z, a[i].ctypes.data_as(C.c_void_p), b[i].ctypes.data_as(C.c_void_p))
             R.ecp_Mod(z)
             assert bytes(z) == out[i].tobytes()
+
+
+def test_comb_index_extraction(engine, oracles, rng):
+    """ecp_8Folds / ecp_4Folds (curve25519_utils.c:144 / :125): the 32 / 64 comb indices of a scalar, against the
+    restatement's folds and the reference's exported functions."""
+    import torch
+    n = 512
+    a = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    a[0] = 0; a[1] = 255; a[2] = np.arange(32, dtype=np.uint8)
+    f8 = engine.test_primitive(12, torch.from_numpy(a).cuda(), out_rec=32).cpu().numpy()
+    f4 = engine.test_primitive(13, torch.from_numpy(a).cuda(), out_rec=64).cpu().numpy()
+    b8 = (C.c_uint8 * 32)(); b4 = (C.c_uint8 * 64)()
+    for i in range(n):
+        oracles["port"].lib.orc_folds8(b8, a[i].ctypes.data_as(C.c_void_p)); assert bytes(b8) == f8[i].tobytes(), i
+        oracles["port"].lib.orc_folds4(b4, a[i].ctypes.data_as(C.c_void_p)); assert bytes(b4) == f4[i].tobytes(), i
+        if "reference" in oracles:
+            oracles["reference"].lib.ecp_8Folds(b8, a[i].ctypes.data_as(C.c_void_p)); assert bytes(b8) == f8[i].tobytes(), i
+            oracles["reference"].lib.ecp_4Folds(b4, a[i].ctypes.data_as(C.c_void_p)); assert bytes(b4) == f4[i].tobytes(), i
