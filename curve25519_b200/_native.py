@@ -29,6 +29,7 @@ def lib():
         "c25519_launch_count": ([], u64),
         "c25519_x25519_shared_batch": ([vp, vp, vp, sz, vp], i32),
         "c25519_x25519_public_batch": ([vp, vp, sz, i32, vp], i32),
+        "c25519_x25519_shared_batch_scatter": ([vp, i32, i32, vp, vp, sz, vp], i32),
         "c25519_x25519_shared_kdf_batch": ([vp, sz, vp, vp, sz, vp], i32),
         "c25519_x25519_scalarmult_raw_batch": ([vp, vp, vp, sz, vp], i32),
         "c25519_x25519_scalarmult_raw_host": ([vp, vp, vp, sz], i32),

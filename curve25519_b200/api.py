@@ -79,6 +79,18 @@ def x25519_shared(pk, sk, out=None, sk_inplace=False):
     return out, skc
 
 
+def x25519_shared_scatter(peer_buffers, rank, pk, sk, sk_inplace=True):
+    """Fused compute + gather: this rank's shared keys are stored by the kernel into row block `rank` of every tensor in
+    peer_buffers (the [world*n_local, 32] gathered arrays of all ranks, peer-mapped; e.g. symmetric-memory buffers)."""
+    pk = _tt(pk, 32); sk = _tt(sk, 32)
+    skc = sk if sk_inplace else sk.clone()
+    world = len(peer_buffers)
+    ptrs = (C.c_void_p * world)(*[C.c_void_p(b.data_ptr()) for b in peer_buffers])
+    check(lib().c25519_x25519_shared_batch_scatter(ptrs, world, int(rank), _p(pk), _p(skc), skc.shape[0], _stream()),
+          "x25519_shared_batch_scatter")
+    return skc
+
+
 def x25519_shared_kdf(pk, sk, key_size=32):
     """X25519Private::CreateSharedKey (C++/x25519.cpp:75-95): SHA-512(shared secret)[:key_size] per record (device tensors)."""
     pk = _tt(pk, 32); skc = _tt(sk, 32).clone()

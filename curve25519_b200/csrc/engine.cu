@@ -199,6 +199,19 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
     return 0;
 }
 
+int c25519_x25519_shared_batch_scatter(uint8_t* const* gathered_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
+                                       size_t n_local, void* stream)
+{
+    if (int rc = check_ready()) return rc;
+    if (!gathered_ptrs || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(C25519_E_BAD_ARGUMENT, "bad world / rank / pointer table");
+    if (n_local && (!pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    for (int g = 0; g < world; g++)
+        if (!gathered_ptrs[g] || misaligned32(gathered_ptrs[g])) return fail(C25519_E_BAD_ARGUMENT, "gathered arrays must be non-null and 32-byte aligned");
+    if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    CK(launch_x25519_ladder_scatter(gathered_ptrs, world, rank, pk32, sk32_inout, n_local, (cudaStream_t)stream));
+    return 0;
+}
+
 int c25519_x25519_shared_kdf_batch(uint8_t* key_out, size_t key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, void* stream)
 {
     if (int rc = check_ready()) return rc;

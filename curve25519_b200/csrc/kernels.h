@@ -18,6 +18,8 @@ extern const uint32_t* g_comb_table_dev;
 
 cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s);
 cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, cudaStream_t s);
+cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
+                                         size_t n_local, cudaStream_t s);
 cudaError_t launch_x25519_shared_kdf(uint8_t* key_out, unsigned key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, cudaStream_t s);
 cudaError_t launch_x25519_comb(uint8_t* pk32, uint8_t* sk32_inout, size_t n, const uint32_t* table, cudaStream_t s);
 cudaError_t launch_ed25519_keypair(uint8_t* pub32, uint8_t* priv64, const uint8_t* seed32, size_t n, const uint32_t* table, cudaStream_t s);

@@ -20,6 +20,15 @@ namespace c25519 {
 constexpr int kScratchXZ = 96;
 constexpr int kScratchXYZ = 128;
 
+// Fused gather: the X25519 result of operation i is stored straight into EVERY rank's copy of the gathered result
+// array (peer-mapped pointers over NVLink / NVSwitch), at row rank * n_local + i, instead of being all-gathered by a
+// separate collective afterwards.
+struct PeerScatter {
+    uint8_t* dst[8];        // device pointers to the [world * n_local, 32] result arrays of ranks 0..world-1 (own included)
+    int world;
+    size_t row_offset;      // rank * n_local
+};
+
 enum NormalizeMode {
     kNormX = 0,        // out32[i] = X/Z                                   (X25519 ladder; comb public key with X = Z+Y, Z = Z-Y)
     kNormEncode = 1,   // out[i * out_stride .. +32) = encode(X/Z, Y/Z); optionally mirrored into out2
@@ -29,7 +38,8 @@ enum NormalizeMode {
 template <int MODE>
 C25519_DEV void normalize_walk(uint8_t* __restrict__ scratch, size_t rec_stride, size_t n, size_t tid, size_t nthreads, int K,
                                uint8_t* __restrict__ out, size_t out_stride, uint8_t* __restrict__ out2, size_t out2_stride,
-                               const uint8_t* __restrict__ cmp, size_t cmp_stride, int32_t* __restrict__ ok)
+                               const uint8_t* __restrict__ cmp, size_t cmp_stride, int32_t* __restrict__ ok,
+                               const PeerScatter* __restrict__ scatter = nullptr)
 {
     constexpr int ZF = (MODE == kNormX) ? 1 : 2;          // field index of Z
     constexpr int PF = ZF + 1;                            // field index of the prefix slot
@@ -68,7 +78,11 @@ C25519_DEV void normalize_walk(uint8_t* __restrict__ scratch, size_t rec_stride,
         fe_mul(x, x, zi);
         fe_canon(x);
         if (MODE == kNormX) {
-            fe_store(out + out_stride * i, x);
+            if (scatter) {
+                for (int g = 0; g < scatter->world; g++) fe_store(scatter->dst[g] + 32 * (scatter->row_offset + i), x);
+            } else {
+                fe_store(out + out_stride * i, x);
+            }
         } else {
             fe y;
             fe_load_plain(y, rec + 32);

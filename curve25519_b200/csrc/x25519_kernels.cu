@@ -129,6 +129,40 @@ k_normalize(uint8_t* __restrict__ scratch, size_t rec_stride, size_t n, size_t n
     normalize_walk<MODE>(scratch, rec_stride, n, tid, nthreads, K, out, out_stride, out2, out2_stride, cmp, cmp_stride, ok);
 }
 
+// X25519 results scattered to all ranks' gathered arrays by the normalisation kernel itself (peer stores).
+__global__ void __launch_bounds__(128)
+k_normalize_scatter(uint8_t* __restrict__ scratch, size_t rec_stride, size_t n, size_t nthreads, int K, PeerScatter sc)
+{
+    const size_t tid = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (tid >= nthreads) return;
+    normalize_walk<kNormX>(scratch, rec_stride, n, tid, nthreads, K, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, &sc);
+}
+
+cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
+                                         size_t n_local, cudaStream_t s)
+{
+    if (n_local == 0) return cudaSuccess;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+    PeerScatter sc; sc.world = world; sc.row_offset = (size_t)rank * n_local;
+    for (int g = 0; g < 8; g++) sc.dst[g] = g < world ? out_ptrs[g] : nullptr;
+    const unsigned grid = (unsigned)((n_local + kLadderThreads - 1) / kLadderThreads);
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, n_local * kScratchXZ, s);
+    if (e != cudaSuccess) return e;
+    k_x25519_ladder<true><<<grid, kLadderThreads, 0, s>>>(nullptr, pk32, sk32_inout, n_local, scratch);
+    count_launch();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        size_t k = n_local / 32768; if (k < 1) k = 1; if (k > 16) k = 16;
+        const size_t nthreads = (n_local + k - 1) / k;
+        k_normalize_scatter<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(scratch, kScratchXZ, n_local, nthreads, (int)k, sc);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size_t n, uint8_t* out, size_t out_stride,
                              uint8_t* out2, size_t out2_stride, const uint8_t* cmp, size_t cmp_stride, int32_t* ok, cudaStream_t s)
 {
