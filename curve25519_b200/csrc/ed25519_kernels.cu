@@ -298,27 +298,17 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
         load_pe(q0, tab + 128 * comb4_index(h, 0));
         ge_from_pe(S, q0);
     }
-    // One doubling and ONE addition routine in the loop body (1 addition for j < 32, 2 for j >= 32): the base-table
-    // entry is fed through the same projective addition with 2 Z2 = 2, which costs one multiplication more than the
-    // dedicated affine addition (+32 M per verification, 1 %) but keeps the loop inside the 32 KB instruction cache --
-    // the first capture of this kernel spent 11 % of its issue slots in "no instruction" stalls
-    // (profiles/r1_verify_check_r1_ncu_summary.txt).  Same sequence of points as edp_PolyPointMultiply.
 #pragma unroll 1
     for (int j = 1; j < 64; j++) {
         ge_double(S);
-        const int first = (j >= 32) ? 0 : 1;
-#pragma unroll 1
-        for (int a = first; a < 2; a++) {
-            ge_pe q;
-            if (a == 0) {                                      // + base_folding8[u[j-32]]   (edp_AddAffinePoint :273)
-                ge_pa qb;
-                comb_load(qb, s_table, comb8_index(s, j - 32));
-                fe_copy(q.ypx, qb.ypx); fe_copy(q.ymx, qb.ymx); fe_copy(q.t2d, qb.t2d); fe_set_u32(q.z2, 2);
-            } else {                                           // + q_table[v[j]]            (edp_AddPoint :266,:274)
-                load_pe(q, tab + 128 * comb4_index(h, j));
-            }
-            ge_add_pe(S, S, q);
+        if (j >= 32) {
+            ge_pa qb;
+            comb_load(qb, s_table, comb8_index(s, j - 32));
+            ge_add_affine(S, qb);
         }
+        ge_pe q;
+        load_pe(q, tab + 128 * comb4_index(h, j));
+        ge_add_pe(S, S, q);
     }
     if (DEFER) { store_xyz(scratch + kScratchXYZ * i, S); return; }     // k_normalize encodes and compares with R
     u32 enc[8];
