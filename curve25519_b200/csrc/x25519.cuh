@@ -29,7 +29,8 @@ C25519_DEV void mont_double(fe& X2, fe& Z2, const fe& X, const fe& Z)
 
 // (S,D) <- (S + D, 2 D) where S - D = (base : 1).      5M + 4S + 1W + 7A     -- the hot loop body
 // SX,SZ,DX,DZ are N (outputs of fe_mul/fe_sqr) on entry and on exit.
-C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
+template <typename BaseLoader>
+C25519_DEV void mont_step_with(fe& SX, fe& SZ, fe& DX, fe& DZ, BaseLoader load_base)
 {
     fe A, B, C, D;
     fe_sub(A, SX, SZ);
@@ -42,7 +43,7 @@ C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
     fe_sub(B, A, B);
     fe_sqr(SX, SX);
     fe_sqr(A, B);
-    fe_mul(SZ, A, base);
+    { fe base; load_base(base); fe_mul(SZ, A, base); }
     fe_sqr(A, D);
     fe_sqr(B, C);
     fe_mul(DX, A, B);
@@ -50,6 +51,9 @@ C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
     fe_mul_small_add(A, A, 121665u, B);
     fe_mul(DZ, A, B);
 }
+
+C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
+{ mont_step_with(SX, SZ, DX, DZ, [&](fe& b) { fe_copy(b, base); }); }
 
 // (PX : PZ) = projective x-coordinate of [k]u.   k must have bit 254 set and bit 255 clear (clamped);
 // kw(w) returns 32-bit word w of k.  The affine result PX/PZ is produced later, for many operations at once,

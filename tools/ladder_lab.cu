@@ -22,6 +22,33 @@ __global__ void __launch_bounds__(T, MINB) k_ladder(uint8_t* __restrict__ out32,
     fe_store(out32+32*i,r);
 }
 
+// base point kept in shared memory (one column per thread) instead of 8 registers
+template<int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_ladder_sb(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, const uint8_t* __restrict__ sk32, size_t n)
+{
+    __shared__ u32 ks[8][T]; __shared__ u32 us[8][T];
+    const size_t i=(size_t)blockIdx.x*T+threadIdx.x; if(i>=n) return;
+    const int t=threadIdx.x;
+    fe k; fe_load(k, sk32+32*i); k.v[0]&=0xfffffff8u; k.v[7]=(k.v[7]|0x40000000u)&0x7fffffffu;
+    #pragma unroll
+    for(int w=0;w<8;w++) ks[w][t]=k.v[w];
+    fe R0X,R0Z,R1X,R1Z;
+    { fe u; fe_load(u, pk32+32*i);
+      #pragma unroll
+      for(int w=0;w<8;w++) us[w][t]=u.v[w];
+      fe_copy(R0X,u); fe_set_u32(R0Z,1); mont_double(R1X,R1Z,R0X,R0Z); fe_narrow(R0X); }
+    bool cur=true;
+    #pragma unroll 1
+    for(int bit=253;bit>=0;--bit){
+        bool b=(ks[bit>>5][t]>>(bit&31))&1u; bool s=(b!=cur);
+        fe_cswap(R0X,R1X,s); fe_cswap(R0Z,R1Z,s); cur=b;
+        mont_step_with(R0X,R0Z,R1X,R1Z,[&](fe& bb){
+            #pragma unroll
+            for(int w=0;w<8;w++) bb.v[w]=us[w][t]; });
+    }
+    fe PX,PZ,zi,r; fe_select(PX,R1X,R0X,cur); fe_select(PZ,R1Z,R0Z,cur); fe_invert(zi,PZ); fe_mul(r,PX,zi); fe_canon(r); fe_store(out32+32*i,r);
+}
+
 // two operations per thread, steps interleaved in one loop body
 template<int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_ladder2(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, const uint8_t* __restrict__ sk32, size_t n)
@@ -77,6 +104,9 @@ int main(int argc,char**argv){
     for(size_t i=0;i<32*c.n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; h[i]=(uint8_t)(s>>24);} cudaMemcpy(c.pk,h.data(),32*c.n,cudaMemcpyHostToDevice);
     for(size_t i=0;i<32*c.n;i++){ s^=s<<13; s^=s>>7; s^=s<<17; h[i]=(uint8_t)(s>>24);} cudaMemcpy(c.sk,h.data(),32*c.n,cudaMemcpyHostToDevice);
     timeit("T128 min1 (ptxas free)", k_ladder<128,1>,128,c.n,c,true);
+    timeit("smem-base T128 min5",    k_ladder_sb<128,5>,128,c.n,c,false);
+    timeit("smem-base T128 min6",    k_ladder_sb<128,6>,128,c.n,c,false);
+    timeit("smem-base T128 min7",    k_ladder_sb<128,7>,128,c.n,c,false);
     timeit("T128 min4 (<=128 regs)", k_ladder<128,4>,128,c.n,c,false);
     timeit("T128 min5 (<=96 regs)",  k_ladder<128,5>,128,c.n,c,false);
     timeit("T128 min6 (<=80 regs)",  k_ladder<128,6>,128,c.n,c,false);
