@@ -240,3 +240,22 @@ def test_device_sc_muladd(engine, rng):
     for i in range(n):
         x = int.from_bytes(a[i].tobytes(), "little"); y = int.from_bytes(b[i].tobytes(), "little")
         assert int.from_bytes(got[i].tobytes(), "little") == (x * y + x) % V.L_ORDER, i
+
+
+def test_long_messages(engine, oracle, rng):
+    """Multi-block hashing on the device: messages of 1 KB .. 64 KB (up to 513 SHA-512 blocks), unaligned starts."""
+    import torch
+    lens = [1000, 4096, 4097, 65535, 65536, 12345, 8191, 3]
+    n = len(lens)
+    seed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    pub, priv = oracle.ed25519_keypair(seed)
+    flat = rng.integers(0, 256, int(sum(lens)), dtype=np.uint8)
+    off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+    exp = oracle.ed25519_sign(priv, flat, off)
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    sig = engine.ed25519_sign(_dev(priv), _dev(flat), d_off)
+    assert (sig.cpu().numpy() == exp).all()
+    bad = exp.copy(); bad[1, 0] ^= 1
+    ok = engine.ed25519_verify(_dev(bad), _dev(pub), _dev(flat), d_off).cpu().numpy()
+    assert ok.tolist() == [1, 0, 1, 1, 1, 1, 1, 1]
+    assert (engine.ed25519_sign(priv, flat, off) == exp).all()

@@ -97,6 +97,11 @@ def test_sha512_kat(oracles):
     out = (C.c_uint8 * 64)()
     lib.orc_sha512(out, b"abc", C.c_size_t(3))
     assert bytes(out).hex() == V.SHA512_ABC
+    # the reference's second SHA-512 KAT: one million 'a' (test/curve25519_selftest.c:131-141)
+    m = b"a" * 1000000
+    lib.orc_sha512(out, m, C.c_size_t(len(m)))
+    assert bytes(out).hex() == ("e718483d0ce769644e2e42c7bc15b4638e1f98b13b2044285632a803afa973eb"
+                                "de0ff244877ea60a4cb0432ce577c31beb009c5c2c49aa2e4eadb217ad8cc09b")
     import hashlib
     rng = np.random.Generator(np.random.PCG64(7))
     for n in (0, 1, 55, 111, 112, 113, 127, 128, 129, 239, 240, 241, 1000):
