@@ -43,6 +43,17 @@ def lib():
         "c25519_ed25519_verify_host": ([vp, vp, vp, vp, vp, sz, sz], i32),
         "c25519_ed25519_verify_init_batch": ([vp, vp, sz, vp], i32),
         "c25519_ed25519_verify_check_batch": ([vp, vp, vp, vp, vp, vp, sz, sz, vp], i32),
+        "c25519_x25519_shared_kdf_host": ([vp, sz, vp, vp, sz], i32),
+        "c25519_modl_batch": ([i32, vp, vp, vp, sz, vp], i32),
+        "c25519_modl_host": ([i32, vp, vp, vp, sz], i32),
+        "c25519_x25519_shared_sharded": ([vp, vp, vp, sz, vp, vp], i32),
+        "c25519_x25519_public_sharded": ([vp, vp, sz, i32, vp, vp], i32),
+        "c25519_ed25519_sign_sharded": ([vp, vp, vp, vp, sz, sz, vp, vp], i32),
+        "c25519_ed25519_verify_sharded": ([vp, vp, vp, vp, vp, sz, sz, vp, vp], i32),
+        "c25519_allgather_records": ([vp, sz, sz, vp, vp], i32),
+        "c25519_nccl_unique_id": ([vp], i32),
+        "c25519_nccl_comm_init": ([C.POINTER(vp), i32, i32, vp, i32], i32),
+        "c25519_nccl_comm_destroy": ([vp], i32),
         "c25519_test_primitive": ([i32, vp, vp, vp, sz, vp], i32),
         "c25519_imad_peak_kernel": ([C.POINTER(u64), vp, i32, vp], i32),
         # the reference's 11-function API (include/c25519_legacy.h)

@@ -41,6 +41,15 @@ def _tt(t, rec=None):
     return t
 
 
+def _np_out(a, n, rec):
+    """A caller-supplied HOST output array is handed to native code as is: it must already be exactly what the C ABI
+    writes -- C-contiguous uint8 [n, rec] (no silent copy: the caller would never see the result)."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.uint8 or a.shape != (n, rec) or not a.flags["C_CONTIGUOUS"] \
+            or not a.flags["WRITEABLE"]:
+        raise ValueError("out must be a writable C-contiguous uint8 array of shape [%d, %d]" % (n, rec))
+    return a
+
+
 def _p(a):
     if _is_dev(a):
         return C.c_void_p(a.data_ptr())
@@ -70,11 +79,15 @@ def x25519_shared(pk, sk, out=None, sk_inplace=False):
         pk = _tt(pk, 32); sk = _tt(sk, 32)
         skc = sk if sk_inplace else sk.clone()
         out = torch.empty_like(skc) if out is None else _tt(out, 32)
+        if pk.shape[0] != skc.shape[0] or out.shape[0] != skc.shape[0]:
+            raise ValueError("pk, sk and out must have the same number of records")
         check(L.c25519_x25519_shared_batch(_p(out), _p(pk), _p(skc), skc.shape[0], _stream()), "x25519_shared_batch")
         return out, skc
     pk = _np(pk, 32); sk = _np(sk, 32)
     skc = sk if sk_inplace else sk.copy()
-    out = np.empty_like(skc) if out is None else out
+    out = np.empty_like(skc) if out is None else _np_out(out, skc.shape[0], 32)
+    if pk.shape[0] != skc.shape[0]:
+        raise ValueError("pk and sk must have the same number of records")
     check(L.c25519_x25519_shared_host(_p(out), _p(pk), _p(skc), skc.shape[0]), "x25519_shared_host")
     return out, skc
 
@@ -92,7 +105,12 @@ def x25519_shared_scatter(peer_buffers, rank, pk, sk, sk_inplace=True):
 
 
 def x25519_shared_kdf(pk, sk, key_size=32):
-    """X25519Private::CreateSharedKey (C++/x25519.cpp:75-95): SHA-512(shared secret)[:key_size] per record (device tensors)."""
+    """X25519Private::CreateSharedKey (C++/x25519.cpp:75-95): SHA-512(shared secret)[:key_size] per record."""
+    if not _is_dev(sk):
+        pk = _np(pk, 32); skc = _np(sk, 32).copy()
+        out = np.empty((skc.shape[0], key_size), np.uint8)
+        check(lib().c25519_x25519_shared_kdf_host(_p(out), key_size, _p(pk), _p(skc), skc.shape[0]), "x25519_shared_kdf_host")
+        return out
     pk = _tt(pk, 32); skc = _tt(sk, 32).clone()
     out = torch.empty((skc.shape[0], key_size), dtype=torch.uint8, device=skc.device)
     check(lib().c25519_x25519_shared_kdf_batch(_p(out), key_size, _p(pk), _p(skc), skc.shape[0], _stream()), "x25519_shared_kdf_batch")
@@ -121,11 +139,13 @@ def x25519_public(sk, ladder=False, out=None, sk_inplace=False):
         sk = _tt(sk, 32)
         skc = sk if sk_inplace else sk.clone()
         out = torch.empty_like(skc) if out is None else _tt(out, 32)
+        if out.shape[0] != skc.shape[0]:
+            raise ValueError("sk and out must have the same number of records")
         check(L.c25519_x25519_public_batch(_p(out), _p(skc), skc.shape[0], int(bool(ladder)), _stream()), "x25519_public_batch")
         return out, skc
     sk = _np(sk, 32)
     skc = sk if sk_inplace else sk.copy()
-    out = np.empty_like(skc) if out is None else out
+    out = np.empty_like(skc) if out is None else _np_out(out, skc.shape[0], 32)
     check(L.c25519_x25519_public_host(_p(out), _p(skc), skc.shape[0], int(bool(ladder))), "x25519_public_host")
     return out, skc
 
@@ -150,6 +170,8 @@ def _msgs_host(msgs, off, n):
 
 
 def _msgs_dev(msgs, off, n):
+    if not _is_dev(msgs) or msgs.dtype != torch.uint8 or not msgs.is_cuda:
+        raise ValueError("messages must be a torch.uint8 CUDA tensor")
     if off is None:
         if msgs.dim() != 2 or msgs.shape[0] != n:
             raise ValueError("fixed-length messages must be uint8 [n, len]")
@@ -157,7 +179,7 @@ def _msgs_dev(msgs, off, n):
         if msgs.numel() == 0:
             msgs = torch.zeros(1, dtype=torch.uint8, device=msgs.device)
         return msgs.contiguous(), None, fixed
-    if off.dtype != torch.int64 and off.dtype != torch.uint64:
+    if not _is_dev(off) or not off.is_cuda or (off.dtype != torch.int64 and off.dtype != torch.uint64) or off.numel() != n + 1:
         raise ValueError("msg_off must be a 64-bit integer CUDA tensor with n+1 entries")
     if msgs.numel() == 0:
         msgs = torch.zeros(1, dtype=torch.uint8, device=off.device)
@@ -233,6 +255,84 @@ def ed25519_verify_check(ctx, sig, msgs, off=None, key_index=None):
                                                   None if off is None else _p(off), fixed, n, _stream()),
           "ed25519_verify_check_batch")
     return ok
+
+
+# ---------------------------------------------------------------------------------------------- mod L
+MODL_MULMOD, MODL_ADDMOD, MODL_MONTMUL, MODL_EXPMOD, MODL_INVMOD = range(5)
+
+
+def modl(op, a, b=None):
+    """Arithmetic modulo the group order on 32-byte little-endian records (the self-test's eco_MulMod / eco_AddMod /
+    eco_MontMul / eco_ExpModBPO / eco_InvModBPO, test/curve25519_selftest.c:160-282); results canonical."""
+    L = lib()
+    if _is_dev(a):
+        a = _tt(a, 32); b = None if b is None else _tt(b, 32)
+        out = torch.empty_like(a)
+        check(L.c25519_modl_batch(int(op), _p(out), _p(a), None if b is None else _p(b), a.shape[0], _stream()), "modl_batch")
+        return out
+    a = _np(a, 32); b = None if b is None else _np(b, 32)
+    out = np.empty_like(a)
+    check(L.c25519_modl_host(int(op), _p(out), _p(a), None if b is None else _p(b), a.shape[0]), "modl_host")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU (NCCL inside the C ABI)
+class ShardedComm:
+    """An ncclComm_t created through the engine's own NCCL binding (c25519_nccl_comm_init), for the *_sharded entry
+    points.  `bootstrap(id_bytes_or_None) -> id_bytes` must hand rank 0's 128-byte unique id to every rank (e.g. a
+    torch.distributed broadcast); the communicator lives on CUDA device `device`."""
+
+    def __init__(self, world, rank, device, bootstrap):
+        L = lib()
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            check(L.c25519_nccl_unique_id(buf), "c25519_nccl_unique_id")
+        uid = bootstrap(bytes(buf) if rank == 0 else None)
+        self.world, self.rank = world, rank
+        self.handle = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        check(L.c25519_nccl_comm_init(C.byref(self.handle), world, rank, idbuf, int(device)), "c25519_nccl_comm_init")
+
+    def close(self):
+        if self.handle:
+            lib().c25519_nccl_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def x25519_shared_sharded(comm, out_all, pk_local, sk_local):
+    """c25519_x25519_shared_sharded: this rank's n_local operations + the NCCL exchange; out_all [world*n_local, 32]."""
+    pk_local = _tt(pk_local, 32); sk_local = _tt(sk_local, 32); out_all = _tt(out_all, 32)
+    n = sk_local.shape[0]
+    if out_all.shape[0] != comm.world * n or pk_local.shape[0] != n:
+        raise ValueError("out_all must hold world * n_local records")
+    check(lib().c25519_x25519_shared_sharded(_p(out_all), _p(pk_local), _p(sk_local), n, comm.handle, _stream()), "x25519_shared_sharded")
+    return out_all
+
+
+def ed25519_sign_sharded(comm, sig_all, priv_local, msgs_local):
+    priv_local = _tt(priv_local, 64); sig_all = _tt(sig_all, 64); n = priv_local.shape[0]
+    msgs, off, fixed = _msgs_dev(msgs_local, None, n)
+    if sig_all.shape[0] != comm.world * n:
+        raise ValueError("sig_all must hold world * n_local records")
+    check(lib().c25519_ed25519_sign_sharded(_p(sig_all), _p(priv_local), _p(msgs), None, fixed, n, comm.handle, _stream()), "ed25519_sign_sharded")
+    return sig_all
+
+
+def ed25519_verify_sharded(comm, ok_all, sig_local, pk_local, msgs_local):
+    sig_local = _tt(sig_local, 64); pk_local = _tt(pk_local, 32); n = sig_local.shape[0]
+    msgs, off, fixed = _msgs_dev(msgs_local, None, n)
+    if ok_all.dtype != torch.int32 or ok_all.numel() != comm.world * n or not ok_all.is_contiguous():
+        raise ValueError("ok_all must be a contiguous int32 tensor of world * n_local entries")
+    check(lib().c25519_ed25519_verify_sharded(_p(ok_all), _p(sig_local), _p(pk_local), _p(msgs), None, fixed, n, comm.handle, _stream()),
+          "ed25519_verify_sharded")
+    return ok_all
+
+
+def allgather_records(comm, all_records, n_local):
+    """In-place NCCL all-gather of fixed-size records (this rank's block already at row rank * n_local)."""
+    rec = all_records.numel() * all_records.element_size() // (comm.world * n_local)
+    check(lib().c25519_allgather_records(_p(all_records), rec, n_local, comm.handle, _stream()), "allgather_records")
+    return all_records
 
 
 # ---------------------------------------------------------------------------------------------- test hooks

@@ -151,9 +151,11 @@ C25519_DEV void msg_span(const uint8_t*& m, u64& len, const uint8_t* msgs, const
 }
 
 // PHASE 0: whole signature in one kernel (private inversion; tiny batches)
-// PHASE 1: [a:b] = H(sk), r = H(b || m) mod L, R = r B projective -> scratch (X, Y, Z, -, a); r parked in sig[32..64)
+// PHASE 1: [a:b] = H(sk), r = H(b || m) mod L, R = r B projective -> private scratch record (X, Y, Z, -, a, r)
 // PHASE 2: (after k_normalize wrote enc(R) to sig[0..32))  h = H(enc(R) || pk || m) mod L,  S = (h a + r) mod L
-constexpr int kSignScratch = 160;                     // X, Y, Z, prefix, a
+// The secret nonce r and scalar a never touch a caller-visible buffer (the reference zeroises both, ed25519_sign.c:417-418);
+// the launcher wipes the scratch before releasing it.
+constexpr int kSignScratch = 192;                     // X, Y, Z, prefix, a, r
 template <int PHASE>
 __global__ void __launch_bounds__(kThreads)
 k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, const uint8_t* __restrict__ msgs,
@@ -185,14 +187,14 @@ k_ed25519_sign(uint8_t* __restrict__ sig64, const uint8_t* __restrict__ priv64, 
             uint8_t* rec = scratch + (size_t)kSignScratch * i;
             store_xyz(rec, S);
             store8(rec + 128, a);
-            store8(sig64 + 64 * i + 32, r);
+            store8(rec + 160, r);
             return;
         }
         ge_encode(enc, S);
     } else {
         load8_plain(enc, sig64 + 64 * i);                       // plain loads: written by earlier launches
-        load8_plain(r, sig64 + 64 * i + 32);
         load8_plain(a, scratch + (size_t)kSignScratch * i + 128);
+        load8_plain(r, scratch + (size_t)kSignScratch * i + 160);
     }
     u32 pk[8], h[8], s[8];
     load8(pk, priv64 + 64 * i + 32);
@@ -308,7 +310,7 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
         }
         ge_pe q;
         load_pe(q, tab + 128 * comb4_index(h, j));
-        ge_add_pe(S, S, q);
+        ge_add_pe<false>(S, S, q);          // followed by a doubling or the end: T is not read again
     }
     if (DEFER) { store_xyz(scratch + kScratchXYZ * i, S); return; }     // k_normalize encodes and compares with R
     u32 enc[8];
@@ -322,15 +324,16 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
 // ---- launchers ----------------------------------------------------------------------------------
 static inline unsigned grid_for(size_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
-// run `body(scratch)` with a stream-ordered scratch buffer of `bytes`
+// run `body(scratch)` with a stream-ordered scratch buffer of `bytes`; `secret` buffers (anything derived from a private
+// key) are wiped before they go back to the pool -- also when a launch inside `body` failed
 template <typename Body>
-static cudaError_t with_scratch(size_t bytes, cudaStream_t s, Body body)
+static cudaError_t with_scratch(size_t bytes, cudaStream_t s, bool secret, Body body)
 {
     uint8_t* scratch = nullptr;
     cudaError_t e = cudaMallocAsync(&scratch, bytes, s);
     if (e != cudaSuccess) return e;
     e = body(scratch);
-    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    cudaError_t e2 = secret ? wipe_and_free(scratch, bytes, s) : cudaFreeAsync(scratch, s);
     return e != cudaSuccess ? e : e2;
 }
 
@@ -342,7 +345,7 @@ cudaError_t launch_x25519_comb(uint8_t* pk32, uint8_t* sk32_inout, size_t n, con
         count_launch();
         return cudaGetLastError();
     }
-    return with_scratch(n * kScratchXZ, s, [&](uint8_t* scratch) {
+    return with_scratch(n * kScratchXZ, s, true, [&](uint8_t* scratch) {
         k_x25519_comb<true><<<grid_for(n), kThreads, 0, s>>>(pk32, sk32_inout, n, table, scratch);
         count_launch();
         cudaError_t e = cudaGetLastError();
@@ -358,7 +361,7 @@ cudaError_t launch_ed25519_keypair(uint8_t* pub32, uint8_t* priv64, const uint8_
         count_launch();
         return cudaGetLastError();
     }
-    return with_scratch(n * kScratchXYZ, s, [&](uint8_t* scratch) {
+    return with_scratch(n * kScratchXYZ, s, true, [&](uint8_t* scratch) {
         k_ed25519_keypair<true><<<grid_for(n), kThreads, 0, s>>>(pub32, priv64, seed32, n, table, scratch);
         count_launch();
         cudaError_t e = cudaGetLastError();
@@ -375,7 +378,7 @@ cudaError_t launch_ed25519_sign(uint8_t* sig64, const uint8_t* priv64, const uin
         count_launch();
         return cudaGetLastError();
     }
-    return with_scratch(n * kSignScratch, s, [&](uint8_t* scratch) {
+    return with_scratch(n * kSignScratch, s, true, [&](uint8_t* scratch) {
         k_ed25519_sign<1><<<grid_for(n), kThreads, 0, s>>>(sig64, priv64, msgs, off, fixed_len, n, table, scratch);
         count_launch();
         cudaError_t e = cudaGetLastError();
@@ -404,7 +407,7 @@ cudaError_t launch_ed25519_verify_check(int32_t* ok, const uint8_t* ctx, const u
         count_launch();
         return cudaGetLastError();
     }
-    return with_scratch(n * kScratchXYZ, s, [&](uint8_t* scratch) {
+    return with_scratch(n * kScratchXYZ, s, false, [&](uint8_t* scratch) {
         k_ed25519_verify_check<true><<<grid_for(n), kThreads, 0, s>>>(ok, ctx, key_index, sig64, msgs, off, fixed_len, n, table, scratch);
         count_launch();
         cudaError_t e = cudaGetLastError();
@@ -414,12 +417,12 @@ cudaError_t launch_ed25519_verify_check(int32_t* ok, const uint8_t* ctx, const u
 }
 
 // Single-phase verification = init + check over a stream-ordered workspace of 2080 B per item, processed in
-// slices so the workspace stays bounded (2^18 items -> 545 MB) however large the batch is.
+// slices so the workspace stays bounded (2^20 items -> 2.2 GB of the 180 GB) however large the batch is.
 cudaError_t launch_ed25519_verify(int32_t* ok, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msgs, const uint64_t* off,
                                   size_t fixed_len, size_t n, const uint32_t* table, cudaStream_t s)
 {
     if (!n) return cudaSuccess;
-    constexpr size_t kSlice = (size_t)1 << 18;
+    constexpr size_t kSlice = (size_t)1 << 20;
     const size_t slice = n < kSlice ? n : kSlice;
     uint8_t* ws = nullptr;
     cudaError_t e = cudaMallocAsync(&ws, slice * kCtxBytes, s);

@@ -1,18 +1,27 @@
 // engine.cu -- host side of the C ABI declared in include/c25519_b200.h and include/c25519_legacy.h.
 //
-// Responsibilities: device selection and one-time upload of the comb table, argument checking, the
-// device-pointer batch entry points (thin: one kernel launch each, asynchronous on the caller's
-// stream), the host-pointer entry points (sliced H2D -> kernel -> D2H pipeline rotating over four
-// private streams, copying straight from/to the caller's buffers), and the reference's 11-function API as n = 1 batches.
+// Responsibilities: per-device state (comb table, staging pipelines, side stream), argument checking, the
+// device-pointer batch entry points (thin: a few kernel launches each, asynchronous on the caller's stream), the
+// host-pointer entry points (sliced H2D -> kernel -> D2H pipeline rotating over four private streams, copying straight
+// from/to the caller's buffers), the multi-GPU entry points (local kernels + one NCCL exchange of result records,
+// overlapped slice by slice), and the reference's C API as n = 1 batches.
 // There is no CPU implementation of any operation in this library: if CUDA is unusable every call fails.
+//
+// Threading (the reference is fully reentrant): no global lock is held while work runs.  Each
+// host-pointer call borrows one Pipeline (private streams + device staging buffers) from a small per-device pool, so
+// concurrent callers overlap on the GPU; device-pointer calls touch no shared mutable state at all.  Every entry point
+// saves and restores the calling thread's current CUDA device.  c25519_shutdown must not race with other calls.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/c25519_b200.h"
 #include "../../include/c25519_legacy.h"
@@ -22,25 +31,34 @@ namespace c25519 {
 
 extern const uint32_t kCombTableHost[kCombEntries * kCombWordsPerEntry];   // comb_table.cu (generated)
 
-const uint32_t* g_comb_table_dev = nullptr;
-
 namespace {
 
-std::mutex g_mu;                       // guards init/shutdown and the host-pointer pipeline
-bool g_ready = false;
-int g_device = -1;
-int g_requested_device = -1;           // set by c25519_init(); -1 = take $C25519_DEVICE, default 0
-std::atomic<uint64_t> g_launches{0};
-thread_local char t_err[256] = "";
+constexpr int kMaxDevices = 64;
+constexpr size_t kChunkOps = 1u << 17;              // operations per pipeline slice
+constexpr int kStages = 4;                          // slices in flight per pipeline (one private stream each)
+constexpr int kMaxPipelines = 4;                    // concurrent host-pointer calls per device before callers queue
+constexpr size_t kRaggedSliceBytes = (size_t)64 << 20;
 
-// host-pointer pipeline resources (grow-only): kStages stages, each a private stream + device scratch
-constexpr size_t kChunkOps = 1u << 17;             // operations per pipeline slice
-constexpr int kStages = 4;                          // slices in flight (one private stream each)
 struct Stage {
     cudaStream_t stream = nullptr;
-    uint8_t* dev = nullptr;  size_t dev_cap = 0;
+    uint8_t* dev = nullptr;  size_t dev_cap = 0;  size_t used = 0;
 };
-Stage g_stage[kStages];
+struct Pipeline { Stage st[kStages]; bool busy = false; };
+
+struct Device {
+    std::atomic<bool> ready{false};
+    const uint32_t* comb = nullptr;                 // device image of the comb table (padded stride)
+    cudaStream_t side = nullptr;                    // side stream for the overlapped NCCL exchange
+    cudaEvent_t ev_slice[8] = {}, ev_done = nullptr;
+    std::mutex mu;                                  // guards `pipes`
+    std::condition_variable cv;
+    std::vector<Pipeline*> pipes;
+};
+Device g_dev[kMaxDevices];
+std::mutex g_init_mu;                               // serialises device initialisation and shutdown
+std::atomic<int> g_default_device{-1};
+std::atomic<uint64_t> g_launches{0};
+thread_local char t_err[256] = "";
 
 int fail(int code, const char* what)
 {
@@ -54,33 +72,97 @@ int fail(int code, const char* what)
         if (e__ != cudaSuccess) return fail((int)e__, #expr);           \
     } while (0)
 
-int ensure_init_locked()
+// Make `dev` current for the lifetime of the guard and put the caller's device back afterwards.
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) { cudaSetDevice(dev); switched = true; }
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_device(int dev)
 {
-    if (g_ready) return 0;
-    int dev = 0;
-    if (g_requested_device >= 0) dev = g_requested_device;
-    else if (const char* e = getenv("C25519_DEVICE")) dev = atoi(e);
+    if (dev < 0 || dev >= kMaxDevices) return fail(C25519_E_BAD_ARGUMENT, "device ordinal out of range");
+    Device& d = g_dev[dev];
+    if (d.ready.load(std::memory_order_acquire)) return 0;
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (d.ready.load(std::memory_order_acquire)) return 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return fail(C25519_E_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)");
-    if (dev < 0 || dev >= count) return fail(C25519_E_BAD_ARGUMENT, "device ordinal out of range");
+    if (dev >= count) return fail(C25519_E_BAD_ARGUMENT, "device ordinal out of range");
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, dev));
     if (p.major != 10) return fail(C25519_E_NO_DEVICE, "device is not compute capability 10.x (kernels are built for sm_100a only)");
-    CK(cudaSetDevice(dev));
+    DeviceGuard g(dev);
     // device image of the comb table: entries padded from 24 to kCombStrideWords (28) words so one TMA bulk
     // copy drops it into shared memory in its bank-conflict-avoiding layout (see ge25519.cuh)
-    static uint32_t padded[kCombEntries * kCombStrideWordsHost];
-    for (int e = 0; e < kCombEntries; e++)
+    std::vector<uint32_t> padded((size_t)kCombEntries * kCombStrideWordsHost);
+    for (int en = 0; en < kCombEntries; en++)
         for (int w = 0; w < kCombStrideWordsHost; w++)
-            padded[e * kCombStrideWordsHost + w] = w < kCombWordsPerEntry ? kCombTableHost[e * kCombWordsPerEntry + w] : 0u;
+            padded[(size_t)en * kCombStrideWordsHost + w] = w < kCombWordsPerEntry ? kCombTableHost[en * kCombWordsPerEntry + w] : 0u;
     uint32_t* t = nullptr;
-    CK(cudaMalloc(&t, sizeof padded));
-    CK(cudaMemcpy(t, padded, sizeof padded, cudaMemcpyHostToDevice));
-    g_comb_table_dev = t;
-    for (auto& st : g_stage) CK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
-    g_device = dev;
-    g_ready = true;
+    CK(cudaMalloc(&t, padded.size() * 4));
+    CK(cudaMemcpy(t, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
+    d.comb = t;
+    CK(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+    for (auto& ev : d.ev_slice) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+    {   // keep the stream-ordered scratch allocations of the launchers cached in the pool between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    int expect = -1;
+    g_default_device.compare_exchange_strong(expect, dev);
+    d.ready.store(true, std::memory_order_release);
+    return 0;
+}
+
+// device used by the host-pointer calls and the legacy wrappers: the first one initialised, else $C25519_DEVICE, else 0
+int default_device(int* dev)
+{
+    int d = g_default_device.load();
+    if (d < 0) { const char* e = getenv("C25519_DEVICE"); d = e ? atoi(e) : 0; }
+    if (int rc = ensure_device(d)) return rc;
+    *dev = d;
+    return 0;
+}
+
+// Device that owns the memory behind `p` (device-pointer entry points).  A pointer that is not device memory of a
+// compute-capability-10 GPU is refused; so are batches whose arrays live on different devices.
+int device_of(const void* p, int* dev)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(C25519_E_NO_DEVICE, "cudaPointerGetAttributes failed: no usable CUDA device (this engine has no CPU fallback)"); }
+    if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)
+        return fail(C25519_E_BAD_ARGUMENT, "*_batch entry points take DEVICE pointers (use the *_host entry points for host memory)");
+    *dev = a.device;
+    return 0;
+}
+int batch_device(int* dev, std::initializer_list<const void*> ptrs)
+{
+    int found = -1;
+    for (const void* p : ptrs) {
+        if (!p) continue;
+        int d = -1;
+        if (int rc = device_of(p, &d)) return rc;
+        if (found >= 0 && d != found) return fail(C25519_E_BAD_ARGUMENT, "record arrays live on different devices");
+        found = d;
+    }
+    if (found < 0) {                                // n == 0 with all-null pointers: nothing will be launched
+        int cnt = 0;
+        if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { cudaGetLastError(); return fail(C25519_E_NO_DEVICE, "no CUDA device (this engine has no CPU fallback)"); }
+        if (cudaGetDevice(&found) != cudaSuccess) found = 0;
+    }
+    if (int rc = ensure_device(found)) return rc;
+    *dev = found;
     return 0;
 }
 
@@ -89,10 +171,47 @@ int reserve(Stage& st, size_t bytes)
     if (st.dev_cap < bytes) {
         if (st.dev) { cudaStreamSynchronize(st.stream); cudaFree(st.dev); }
         st.dev = nullptr; st.dev_cap = 0;
-        if (cudaMalloc(&st.dev, bytes) != cudaSuccess) return fail(C25519_E_OUT_OF_MEMORY, "cudaMalloc(stage)");
+        if (cudaMalloc(&st.dev, bytes) != cudaSuccess) { cudaGetLastError(); return fail(C25519_E_OUT_OF_MEMORY, "cudaMalloc(stage)"); }
         st.dev_cap = bytes;
     }
     return 0;
+}
+
+// Borrow a pipeline of device `d` (the device must be current: new pipelines create streams).
+Pipeline* acquire(Device& d)
+{
+    std::unique_lock<std::mutex> lk(d.mu);
+    for (;;) {
+        for (Pipeline* p : d.pipes) if (!p->busy) { p->busy = true; return p; }
+        if ((int)d.pipes.size() < kMaxPipelines) {
+            Pipeline* p = new Pipeline();
+            bool ok = true;
+            for (auto& st : p->st) ok = ok && cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) == cudaSuccess;
+            if (!ok) { for (auto& st : p->st) if (st.stream) cudaStreamDestroy(st.stream); delete p; return nullptr; }
+            p->busy = true;
+            d.pipes.push_back(p);
+            return p;
+        }
+        d.cv.wait(lk);
+    }
+}
+void release(Device& d, Pipeline* p)
+{
+    { std::lock_guard<std::mutex> lk(d.mu); p->busy = false; }
+    d.cv.notify_one();
+}
+// drain every stage (also on the error path: queued copies may still touch the caller's buffers), optionally wiping
+// the staging memory that held secret keys / shared secrets first
+int drain(Pipeline* p, bool wipe)
+{
+    int rc = 0;
+    for (auto& st : p->st) {
+        if (wipe && st.dev && st.used) cudaMemsetAsync(st.dev, 0, std::min(st.used, st.dev_cap), st.stream);
+        cudaError_t e = cudaStreamSynchronize(st.stream);
+        if (e != cudaSuccess && rc == 0) rc = fail((int)e, "cudaStreamSynchronize(stage)");
+        st.used = 0;
+    }
+    return rc;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -103,15 +222,18 @@ struct Field { size_t rec; bool in, out; const uint8_t* src; uint8_t* dst; };
 // Generic chunked pipeline.  For each chunk: H2D the `in` fields straight from the caller's buffers
 // (truly asynchronous when they are pinned, driver-staged when pageable), run `launch` on the device
 // copies, D2H the `out` fields straight into the caller's buffers.  kStages stages on as many streams rotate,
-// so slice c+1's H2D overlaps slice c's kernel and slice c-1's D2H (both PCIe directions busy); stream order protects the reuse of a
-// stage's device scratch.  Returns after both streams have drained.
+// so slice c+1's H2D overlaps slice c's kernel and slice c-1's D2H (both PCIe directions busy); stream order protects
+// the reuse of a stage's device scratch.  Returns after every stream has drained -- on failure too.
 template <int NF, typename Launch>
-int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
+int run_host_pipeline(Field (&f)[NF], size_t n, bool secret, Launch launch)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = ensure_init_locked()) return rc;
-    CK(cudaSetDevice(g_device));
+    int dev = 0;
+    if (int rc = default_device(&dev)) return rc;
     if (n == 0) return 0;
+    DeviceGuard g(dev);
+    Device& D = g_dev[dev];
+    Pipeline* P = acquire(D);
+    if (!P) return fail(C25519_E_OUT_OF_MEMORY, "cannot create pipeline streams");
     size_t rec_total = 0;
     for (int k = 0; k < NF; k++) rec_total += f[k].rec;
     // slice size: 2^17 operations, fewer when records are large (long messages) so a stage stays <= 256 MB
@@ -119,32 +241,113 @@ int run_host_pipeline(Field (&f)[NF], size_t n, Launch launch)
     const size_t chunk = std::min(n, std::min(kChunkOps, by_bytes));
     size_t offs[NF + 1]; offs[0] = 0;
     for (int k = 0; k < NF; k++) offs[k + 1] = offs[k] + align_up(f[k].rec * chunk, 256);
-    for (auto& st : g_stage) if (int rc = reserve(st, offs[NF])) return rc;
-    int s = 0;
-    for (size_t base = 0; base < n; base += chunk, s = (s + 1) % kStages) {
-        const size_t cnt = std::min(chunk, n - base);
-        Stage& st = g_stage[s];
-        uint8_t* d[NF];
-        for (int k = 0; k < NF; k++) {
-            d[k] = st.dev + offs[k];
-            if (f[k].in) CK(cudaMemcpyAsync(d[k], f[k].src + f[k].rec * base, f[k].rec * cnt, cudaMemcpyHostToDevice, st.stream));
+    int rc = 0;
+    auto body = [&]() -> int {
+        for (auto& st : P->st) if (int r = reserve(st, offs[NF])) return r;
+        int s = 0;
+        for (size_t base = 0; base < n; base += chunk, s = (s + 1) % kStages) {
+            const size_t cnt = std::min(chunk, n - base);
+            Stage& st = P->st[s];
+            st.used = offs[NF];
+            uint8_t* d[NF];
+            for (int k = 0; k < NF; k++) {
+                d[k] = st.dev + offs[k];
+                if (f[k].in) CK(cudaMemcpyAsync(d[k], f[k].src + f[k].rec * base, f[k].rec * cnt, cudaMemcpyHostToDevice, st.stream));
+            }
+            CK(launch(d, cnt, st.stream, D));
+            for (int k = 0; k < NF; k++)
+                if (f[k].out) CK(cudaMemcpyAsync(f[k].dst + f[k].rec * base, d[k], f[k].rec * cnt, cudaMemcpyDeviceToHost, st.stream));
         }
-        CK(launch(d, cnt, st.stream));
-        for (int k = 0; k < NF; k++)
-            if (f[k].out) CK(cudaMemcpyAsync(f[k].dst + f[k].rec * base, d[k], f[k].rec * cnt, cudaMemcpyDeviceToHost, st.stream));
-    }
-    for (auto& st : g_stage) CK(cudaStreamSynchronize(st.stream));
-    return 0;
+        return 0;
+    };
+    rc = body();
+    char saved[sizeof t_err]; memcpy(saved, t_err, sizeof saved);
+    int rc2 = drain(P, secret);
+    if (rc) memcpy(t_err, saved, sizeof saved);        // keep the first failure's message
+    release(D, P);
+    return rc ? rc : rc2;
 }
 
 inline bool misaligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) != 0; }
 
-int check_ready()
+// ---- NCCL, bound at run time (dlopen) so the library loads on hosts without NCCL; the sharded calls then fail loudly ----
+typedef struct { char internal[128]; } nccl_uid;
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*CommCount)(void*, int*) = nullptr;
+    int (*CommUserRank)(void*, int*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+Nccl g_nccl;
+std::once_flag g_nccl_once;
+constexpr int kNcclUint8 = 1;                        // ncclUint8 (nccl.h: ncclInt8 = 0, ncclUint8 = 1)
+
+int nccl_load()
 {
-    if (!g_ready) {
-        std::lock_guard<std::mutex> lk(g_mu);
-        return ensure_init_locked();
+    std::call_once(g_nccl_once, [] {
+        const char* names[] = {getenv("C25519_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm) continue;
+            g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.h) break;
+        }
+        if (!g_nccl.h) return;
+        auto sym = [&](const char* s) { return dlsym(g_nccl.h, s); };
+#define BIND(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(sym(name))
+        BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
+        BIND(CommCount, "ncclCommCount"); BIND(CommUserRank, "ncclCommUserRank"); BIND(AllGather, "ncclAllGather");
+        BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv"); BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd");
+        BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+        g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.CommCount && g_nccl.CommUserRank &&
+                    g_nccl.AllGather && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+    });
+    if (!g_nccl.ok) return fail(C25519_E_NO_NCCL, "NCCL is not available (libnccl.so.2 not found; set C25519_NCCL_LIB)");
+    return 0;
+}
+int nccl_fail(int code, const char* what)
+{
+    snprintf(t_err, sizeof t_err, "%s: NCCL error %d (%s)", what, code, g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "?");
+    return C25519_E_NCCL;
+}
+#define NK(expr)                                                        \
+    do {                                                                \
+        int r__ = (expr);                                               \
+        if (r__ != 0) return nccl_fail(r__, #expr);                     \
+    } while (0)
+
+int comm_shape(void* comm, int* world, int* rank)
+{
+    if (int rc = nccl_load()) return rc;
+    if (!comm) return fail(C25519_E_BAD_ARGUMENT, "null NCCL communicator");
+    NK(g_nccl.CommCount(comm, world));
+    NK(g_nccl.CommUserRank(comm, rank));
+    return 0;
+}
+
+// exchange `cnt` records of `rec` bytes starting at row `row0` of every rank's block of `all` ([world][n_local] records)
+int exchange_rows(uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t cnt, int world, int rank, void* comm, cudaStream_t s)
+{
+    if (row0 == 0 && cnt == n_local) {               // whole blocks: the plain in-place all-gather
+        NK(g_nccl.AllGather(all + (size_t)rank * n_local * rec, all, n_local * rec, kNcclUint8, comm, s));
+        return 0;
     }
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < world; p++) {
+        if (p == rank) continue;
+        NK(g_nccl.Send(all + ((size_t)rank * n_local + row0) * rec, cnt * rec, kNcclUint8, p, comm, s));
+        NK(g_nccl.Recv(all + ((size_t)p * n_local + row0) * rec, cnt * rec, kNcclUint8, p, comm, s));
+    }
+    NK(g_nccl.GroupEnd());
     return 0;
 }
 
@@ -160,29 +363,34 @@ extern "C" {
 
 int c25519_init(int device)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_ready && device == g_device) return 0;
-    if (g_ready) return fail(C25519_E_BAD_ARGUMENT, "already initialised on another device; call c25519_shutdown first");
     if (device < 0) return fail(C25519_E_BAD_ARGUMENT, "device ordinal must be >= 0");
-    g_requested_device = device;
-    return ensure_init_locked();
+    return ensure_device(device);
 }
 
 int c25519_shutdown(void)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_ready) return 0;
-    cudaSetDevice(g_device);
-    cudaDeviceSynchronize();
-    for (auto& st : g_stage) {
-        if (st.dev) cudaFree(st.dev);
-        if (st.stream) cudaStreamDestroy(st.stream);
-        st = Stage();
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (int dev = 0; dev < kMaxDevices; dev++) {
+        Device& d = g_dev[dev];
+        if (!d.ready.load()) continue;
+        DeviceGuard g(dev);
+        cudaDeviceSynchronize();
+        {
+            std::lock_guard<std::mutex> lk2(d.mu);
+            for (Pipeline* p : d.pipes) {
+                for (auto& st : p->st) { if (st.dev) cudaFree(st.dev); if (st.stream) cudaStreamDestroy(st.stream); }
+                delete p;
+            }
+            d.pipes.clear();
+        }
+        for (auto& ev : d.ev_slice) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+        if (d.ev_done) { cudaEventDestroy(d.ev_done); d.ev_done = nullptr; }
+        if (d.side) { cudaStreamDestroy(d.side); d.side = nullptr; }
+        cudaFree(const_cast<uint32_t*>(d.comb));
+        d.comb = nullptr;
+        d.ready.store(false);
     }
-    cudaFree(const_cast<uint32_t*>(g_comb_table_dev));
-    g_comb_table_dev = nullptr;
-    g_ready = false;
-    g_requested_device = -1;
+    g_default_device.store(-1);
     return 0;
 }
 
@@ -190,11 +398,18 @@ const char* c25519_last_error(void) { return t_err; }
 uint64_t c25519_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------ device-pointer batch API
+#define BATCH_PROLOGUE(...)                                             \
+    int dev__ = 0;                                                      \
+    if (int rc = batch_device(&dev__, {__VA_ARGS__})) return rc;        \
+    DeviceGuard guard__(dev__);                                         \
+    Device& D = g_dev[dev__];                                           \
+    (void)D
+
 int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(out32) || misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(out32, pk32, sk32_inout);
     CK(launch_x25519_ladder(out32, pk32, sk32_inout, n, (cudaStream_t)stream));
     return 0;
 }
@@ -202,79 +417,79 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
 int c25519_x25519_shared_batch_scatter(uint8_t* const* gathered_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
                                        size_t n_local, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (!gathered_ptrs || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(C25519_E_BAD_ARGUMENT, "bad world / rank / pointer table");
     if (n_local && (!pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     for (int g = 0; g < world; g++)
         if (!gathered_ptrs[g] || misaligned32(gathered_ptrs[g])) return fail(C25519_E_BAD_ARGUMENT, "gathered arrays must be non-null and 32-byte aligned");
     if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(pk32, sk32_inout, gathered_ptrs[rank]);     // peers' arrays live on other devices by design
     CK(launch_x25519_ladder_scatter(gathered_ptrs, world, rank, pk32, sk32_inout, n_local, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_x25519_shared_kdf_batch(uint8_t* key_out, size_t key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!key_out || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (key_size == 0 || key_size > 64) return fail(C25519_E_BAD_ARGUMENT, "key_size must be 1..64 (bytes of the SHA-512 digest)");
     if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(key_out, pk32, sk32_inout);
     CK(launch_x25519_shared_kdf(key_out, (unsigned)key_size, pk32, sk32_inout, n, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_x25519_scalarmult_raw_batch(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!out32 || !point32 || !scalar32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(out32) || misaligned32(point32) || misaligned32(scalar32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(out32, point32, scalar32);
     CK(launch_x25519_ladder_raw(out32, point32, scalar32, n, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_x25519_public_batch(uint8_t* pk32, uint8_t* sk32_inout, size_t n, int ladder, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(pk32, sk32_inout);
     if (ladder) CK(launch_x25519_ladder(pk32, nullptr, sk32_inout, n, (cudaStream_t)stream));
-    else CK(launch_x25519_comb(pk32, sk32_inout, n, g_comb_table_dev, (cudaStream_t)stream));
+    else CK(launch_x25519_comb(pk32, sk32_inout, n, D.comb, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_ed25519_keypair_batch(uint8_t* pub32, uint8_t* priv64, const uint8_t* seed32, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!pub32 || !priv64 || !seed32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(pub32) || misaligned32(priv64) || misaligned32(seed32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
-    CK(launch_ed25519_keypair(pub32, priv64, seed32, n, g_comb_table_dev, (cudaStream_t)stream));
+    BATCH_PROLOGUE(pub32, priv64, seed32);
+    CK(launch_ed25519_keypair(pub32, priv64, seed32, n, D.comb, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_ed25519_sign_batch(uint8_t* sig64, const uint8_t* priv64, const uint8_t* msgs, const uint64_t* msg_off,
                               size_t fixed_len, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!sig64 || !priv64)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(sig64) || misaligned32(priv64)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
-    CK(launch_ed25519_sign(sig64, priv64, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
+    BATCH_PROLOGUE(sig64, priv64, msg_off);
+    CK(launch_ed25519_sign(sig64, priv64, msgs, msg_off, fixed_len, n, D.comb, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_ed25519_verify_batch(int32_t* ok, const uint8_t* sig64, const uint8_t* pk32, const uint8_t* msgs,
                                 const uint64_t* msg_off, size_t fixed_len, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!ok || !sig64 || !pk32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(sig64) || misaligned32(pk32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
-    CK(launch_ed25519_verify(ok, sig64, pk32, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
+    BATCH_PROLOGUE(ok, sig64, pk32);
+    CK(launch_ed25519_verify(ok, sig64, pk32, msgs, msg_off, fixed_len, n, D.comb, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_ed25519_verify_init_batch(uint8_t* ctx, const uint8_t* pk32, size_t n_keys, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n_keys && (!ctx || !pk32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(ctx) || misaligned32(pk32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(ctx, pk32);
     CK(launch_ed25519_verify_init(ctx, pk32, n_keys, (cudaStream_t)stream));
     return 0;
 }
@@ -282,25 +497,149 @@ int c25519_ed25519_verify_init_batch(uint8_t* ctx, const uint8_t* pk32, size_t n
 int c25519_ed25519_verify_check_batch(int32_t* ok, const uint8_t* ctx, const uint32_t* key_index, const uint8_t* sig64,
                                       const uint8_t* msgs, const uint64_t* msg_off, size_t fixed_len, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
     if (n && (!ok || !ctx || !sig64)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(ctx) || misaligned32(sig64)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
-    CK(launch_ed25519_verify_check(ok, ctx, key_index, sig64, msgs, msg_off, fixed_len, n, g_comb_table_dev, (cudaStream_t)stream));
+    BATCH_PROLOGUE(ok, ctx, sig64);
+    CK(launch_ed25519_verify_check(ok, ctx, key_index, sig64, msgs, msg_off, fixed_len, n, D.comb, (cudaStream_t)stream));
+    return 0;
+}
+
+int c25519_modl_batch(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n, void* stream)
+{
+    if (op < C25519_MODL_MULMOD || op > C25519_MODL_INVMOD) return fail(C25519_E_BAD_ARGUMENT, "unknown mod-L operation");
+    if (n && (!out32 || !a32 || (op != C25519_MODL_INVMOD && !b32))) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(out32) || misaligned32(a32) || misaligned32(b32)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(out32, a32, b32);
+    CK(launch_modl(op, out32, a32, b32, n, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, void* stream)
 {
-    if (int rc = check_ready()) return rc;
+    BATCH_PROLOGUE(out, a, b);
     CK(launch_test_primitive(op, out, a, b, n, (cudaStream_t)stream));
     return 0;
 }
 
 int c25519_imad_peak_kernel(uint64_t* mac_per_launch, uint32_t* sink, int iters, void* stream)
 {
-    if (int rc = check_ready()) return rc;
+    BATCH_PROLOGUE(sink);
     CK(launch_imad_peak(mac_per_launch, sink, iters, (cudaStream_t)stream));
     return 0;
+}
+
+// ------------------------------------------------------------------ multi-GPU: local kernels + ONE NCCL exchange of results
+int c25519_nccl_unique_id(void* id128)
+{
+    if (int rc = nccl_load()) return rc;
+    if (!id128) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    nccl_uid u;
+    NK(g_nccl.GetUniqueId(&u));
+    memcpy(id128, &u, sizeof u);
+    return 0;
+}
+
+int c25519_nccl_comm_init(void** comm, int world, int rank, const void* id128, int device)
+{
+    if (int rc = nccl_load()) return rc;
+    if (!comm || !id128 || world < 1 || rank < 0 || rank >= world) return fail(C25519_E_BAD_ARGUMENT, "bad communicator arguments");
+    if (int rc = ensure_device(device)) return rc;
+    DeviceGuard g(device);
+    nccl_uid u; memcpy(&u, id128, sizeof u);
+    NK(g_nccl.CommInitRank(comm, world, u, rank));
+    return 0;
+}
+
+int c25519_nccl_comm_destroy(void* comm)
+{
+    if (int rc = nccl_load()) return rc;
+    if (comm) NK(g_nccl.CommDestroy(comm));
+    return 0;
+}
+
+int c25519_allgather_records(void* all, size_t rec_bytes, size_t n_local, void* nccl_comm, void* stream)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (n_local == 0 || rec_bytes == 0) return 0;
+    if (!all) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    BATCH_PROLOGUE(all);
+    return exchange_rows(static_cast<uint8_t*>(all), rec_bytes, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream);
+}
+
+// X25519 shared keys, sharded: this rank computes rows [rank*n_local, (rank+1)*n_local) of out_all and receives the other
+// ranks' rows.  The local batch is cut into up to four slices; slice i's exchange runs on a side stream underneath slice
+// i+1's ladder, so only the last slice's transfer is exposed.
+int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, uint8_t* sk32_local_inout, size_t n_local,
+                                 void* nccl_comm, void* stream)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (n_local == 0) return 0;
+    if (!out_all || !pk32_local || !sk32_local_inout) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(out_all) || misaligned32(pk32_local) || misaligned32(sk32_local_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(out_all, pk32_local, sk32_local_inout);
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* mine = out_all + (size_t)rank * n_local * 32;
+    const int slices = world == 1 ? 1 : (n_local >= ((size_t)1 << 18) ? 4 : (n_local >= ((size_t)1 << 16) ? 2 : 1));
+    if (slices == 1) {
+        CK(launch_x25519_ladder(mine, pk32_local, sk32_local_inout, n_local, s));
+        if (world > 1) return exchange_rows(out_all, 32, n_local, 0, n_local, world, rank, nccl_comm, s);
+        return 0;
+    }
+    const size_t per = (n_local + slices - 1) / slices;
+    for (int i = 0; i < slices; i++) {
+        const size_t row0 = (size_t)i * per;
+        if (row0 >= n_local) break;
+        const size_t cnt = std::min(per, n_local - row0);
+        CK(launch_x25519_ladder(mine + 32 * row0, pk32_local + 32 * row0, sk32_local_inout + 32 * row0, cnt, s));
+        CK(cudaEventRecord(D.ev_slice[i], s));
+        CK(cudaStreamWaitEvent(D.side, D.ev_slice[i], 0));
+        if (int rc = exchange_rows(out_all, 32, n_local, row0, cnt, world, rank, nccl_comm, D.side)) return rc;
+    }
+    CK(cudaEventRecord(D.ev_done, D.side));
+    CK(cudaStreamWaitEvent(s, D.ev_done, 0));
+    return 0;
+}
+
+int c25519_x25519_public_sharded(uint8_t* pk_all, uint8_t* sk32_local_inout, size_t n_local, int ladder, void* nccl_comm, void* stream)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (n_local == 0) return 0;
+    if (!pk_all || !sk32_local_inout) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(pk_all) || misaligned32(sk32_local_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(pk_all, sk32_local_inout);
+    uint8_t* mine = pk_all + (size_t)rank * n_local * 32;
+    if (ladder) CK(launch_x25519_ladder(mine, nullptr, sk32_local_inout, n_local, (cudaStream_t)stream));
+    else CK(launch_x25519_comb(mine, sk32_local_inout, n_local, D.comb, (cudaStream_t)stream));
+    return world > 1 ? exchange_rows(pk_all, 32, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
+}
+
+int c25519_ed25519_sign_sharded(uint8_t* sig_all, const uint8_t* priv64_local, const uint8_t* msgs_local, const uint64_t* msg_off_local,
+                                size_t fixed_len, size_t n_local, void* nccl_comm, void* stream)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (n_local == 0) return 0;
+    if (!sig_all || !priv64_local) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(sig_all) || misaligned32(priv64_local)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(sig_all, priv64_local);
+    CK(launch_ed25519_sign(sig_all + (size_t)rank * n_local * 64, priv64_local, msgs_local, msg_off_local, fixed_len, n_local, D.comb, (cudaStream_t)stream));
+    return world > 1 ? exchange_rows(sig_all, 64, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
+}
+
+int c25519_ed25519_verify_sharded(int32_t* ok_all, const uint8_t* sig64_local, const uint8_t* pk32_local, const uint8_t* msgs_local,
+                                  const uint64_t* msg_off_local, size_t fixed_len, size_t n_local, void* nccl_comm, void* stream)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (n_local == 0) return 0;
+    if (!ok_all || !sig64_local || !pk32_local) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (misaligned32(sig64_local) || misaligned32(pk32_local)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
+    BATCH_PROLOGUE(ok_all, sig64_local, pk32_local);
+    CK(launch_ed25519_verify(ok_all + (size_t)rank * n_local, sig64_local, pk32_local, msgs_local, msg_off_local, fixed_len, n_local, D.comb, (cudaStream_t)stream));
+    return world > 1 ? exchange_rows(reinterpret_cast<uint8_t*>(ok_all), 4, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
 }
 
 // ------------------------------------------------------------------ host-pointer batch API
@@ -308,22 +647,32 @@ int c25519_x25519_shared_host(uint8_t* out32, const uint8_t* pk32, uint8_t* sk32
 {
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     Field f[3] = {{32, false, true, nullptr, out32}, {32, true, false, pk32, nullptr}, {32, true, true, sk32_inout, sk32_inout}};
-    return run_host_pipeline(f, n, [](uint8_t** d, size_t cnt, cudaStream_t s) { return launch_x25519_ladder(d[0], d[1], d[2], cnt, s); });
+    return run_host_pipeline(f, n, true, [](uint8_t** d, size_t cnt, cudaStream_t s, Device&) { return launch_x25519_ladder(d[0], d[1], d[2], cnt, s); });
 }
 
 int c25519_x25519_scalarmult_raw_host(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n)
 {
     if (n && (!out32 || !point32 || !scalar32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     Field f[3] = {{32, false, true, nullptr, out32}, {32, true, false, point32, nullptr}, {32, true, false, scalar32, nullptr}};
-    return run_host_pipeline(f, n, [](uint8_t** d, size_t cnt, cudaStream_t s) { return launch_x25519_ladder_raw(d[0], d[1], d[2], cnt, s); });
+    return run_host_pipeline(f, n, true, [](uint8_t** d, size_t cnt, cudaStream_t s, Device&) { return launch_x25519_ladder_raw(d[0], d[1], d[2], cnt, s); });
 }
 
 int c25519_x25519_public_host(uint8_t* pk32, uint8_t* sk32_inout, size_t n, int ladder)
 {
     if (n && (!pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     Field f[2] = {{32, false, true, nullptr, pk32}, {32, true, true, sk32_inout, sk32_inout}};
-    return run_host_pipeline(f, n, [ladder](uint8_t** d, size_t cnt, cudaStream_t s) {
-        return ladder ? launch_x25519_ladder(d[0], nullptr, d[1], cnt, s) : launch_x25519_comb(d[0], d[1], cnt, g_comb_table_dev, s);
+    return run_host_pipeline(f, n, true, [ladder](uint8_t** d, size_t cnt, cudaStream_t s, Device& D) {
+        return ladder ? launch_x25519_ladder(d[0], nullptr, d[1], cnt, s) : launch_x25519_comb(d[0], d[1], cnt, D.comb, s);
+    });
+}
+
+int c25519_x25519_shared_kdf_host(uint8_t* key_out, size_t key_size, const uint8_t* pk32, uint8_t* sk32_inout, size_t n)
+{
+    if (n && (!key_out || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    if (key_size == 0 || key_size > 64) return fail(C25519_E_BAD_ARGUMENT, "key_size must be 1..64 (bytes of the SHA-512 digest)");
+    Field f[3] = {{key_size, false, true, nullptr, key_out}, {32, true, false, pk32, nullptr}, {32, true, true, sk32_inout, sk32_inout}};
+    return run_host_pipeline(f, n, true, [key_size](uint8_t** d, size_t cnt, cudaStream_t s, Device&) {
+        return launch_x25519_shared_kdf(d[0], (unsigned)key_size, d[1], d[2], cnt, s);
     });
 }
 
@@ -331,13 +680,26 @@ int c25519_ed25519_keypair_host(uint8_t* pub32, uint8_t* priv64, const uint8_t* 
 {
     if (n && (!pub32 || !priv64 || !seed32)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     Field f[3] = {{32, false, true, nullptr, pub32}, {64, false, true, nullptr, priv64}, {32, true, false, seed32, nullptr}};
-    return run_host_pipeline(f, n, [](uint8_t** d, size_t cnt, cudaStream_t s) {
-        return launch_ed25519_keypair(d[0], d[1], d[2], cnt, g_comb_table_dev, s);
+    return run_host_pipeline(f, n, true, [](uint8_t** d, size_t cnt, cudaStream_t s, Device& D) {
+        return launch_ed25519_keypair(d[0], d[1], d[2], cnt, D.comb, s);
     });
 }
 
-// Ragged messages are staged as one extra blob per call (not chunked): the fixed-length fast path is the
-// one the throughput configurations use.
+int c25519_modl_host(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n)
+{
+    if (op < C25519_MODL_MULMOD || op > C25519_MODL_INVMOD) return fail(C25519_E_BAD_ARGUMENT, "unknown mod-L operation");
+    if (n && (!out32 || !a32 || (op != C25519_MODL_INVMOD && !b32))) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
+    const bool two = b32 != nullptr;
+    Field f[3] = {{32, false, true, nullptr, out32}, {32, true, false, a32, nullptr}, {32, two, false, b32, nullptr}};
+    return run_host_pipeline(f, n, true, [op, two](uint8_t** d, size_t cnt, cudaStream_t s, Device&) {
+        return launch_modl(op, d[0], d[1], two ? d[2] : nullptr, cnt, s);
+    });
+}
+
+// Ed25519 with messages.  Fixed-length messages ride the generic pipeline as one more record field.  Ragged messages are
+// sliced by operation count AND message bytes (<= 64 MB of message data per slice unless a single message is larger), each
+// slice staged through a pipeline stage: offsets are uploaded unmodified and the kernels get a message base pointer
+// shifted back by the slice's first offset, so nothing is rebased on the host.
 static int ed25519_host_msgs(bool sign, uint8_t* out, const uint8_t* in64, const uint8_t* pk32, const uint8_t* msgs,
                              const uint64_t* msg_off, size_t fixed_len, size_t n)
 {
@@ -345,47 +707,57 @@ static int ed25519_host_msgs(bool sign, uint8_t* out, const uint8_t* in64, const
         const size_t ml = fixed_len ? fixed_len : 1;   // zero-length records still need a non-zero stride for staging
         if (sign) {
             Field f[3] = {{64, false, true, nullptr, out}, {64, true, false, in64, nullptr}, {ml, fixed_len != 0, false, msgs, nullptr}};
-            return run_host_pipeline(f, n, [fixed_len](uint8_t** d, size_t cnt, cudaStream_t s) {
-                return launch_ed25519_sign(d[0], d[1], d[2], nullptr, fixed_len, cnt, g_comb_table_dev, s);
+            return run_host_pipeline(f, n, true, [fixed_len](uint8_t** d, size_t cnt, cudaStream_t s, Device& D) {
+                return launch_ed25519_sign(d[0], d[1], d[2], nullptr, fixed_len, cnt, D.comb, s);
             });
         }
         Field f[4] = {{4, false, true, nullptr, out}, {64, true, false, in64, nullptr}, {32, true, false, pk32, nullptr},
                       {ml, fixed_len != 0, false, msgs, nullptr}};
-        return run_host_pipeline(f, n, [fixed_len](uint8_t** d, size_t cnt, cudaStream_t s) {
-            return launch_ed25519_verify(reinterpret_cast<int32_t*>(d[0]), d[1], d[2], d[3], nullptr, fixed_len, cnt, g_comb_table_dev, s);
+        return run_host_pipeline(f, n, false, [fixed_len](uint8_t** d, size_t cnt, cudaStream_t s, Device& D) {
+            return launch_ed25519_verify(reinterpret_cast<int32_t*>(d[0]), d[1], d[2], d[3], nullptr, fixed_len, cnt, D.comb, s);
         });
     }
-    // ragged: single shot on stage 0's stream with ad-hoc device buffers
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = ensure_init_locked()) return rc;
-    CK(cudaSetDevice(g_device));
+    int dev = 0;
+    if (int rc = default_device(&dev)) return rc;
     if (n == 0) return 0;
-    const size_t total = (size_t)msg_off[n];
+    DeviceGuard g(dev);
+    Device& D = g_dev[dev];
+    Pipeline* P = acquire(D);
+    if (!P) return fail(C25519_E_OUT_OF_MEMORY, "cannot create pipeline streams");
     const size_t out_rec = sign ? 64 : 4;
-    uint8_t *d_out = nullptr, *d_in = nullptr, *d_pk = nullptr, *d_msgs = nullptr; uint64_t* d_off = nullptr;
-    cudaStream_t s = g_stage[0].stream;
-    int rc = 0;
-    auto cleanup = [&]() { cudaFree(d_out); cudaFree(d_in); cudaFree(d_pk); cudaFree(d_msgs); cudaFree(d_off); };
-#define CKC(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = fail((int)e__, #expr); cleanup(); return rc; } } while (0)
-    CKC(cudaMalloc(&d_out, out_rec * n));
-    CKC(cudaMalloc(&d_in, 64 * n));
-    CKC(cudaMalloc(&d_msgs, total ? total : 1));
-    CKC(cudaMalloc(&d_off, 8 * (n + 1)));
-    CKC(cudaMemcpyAsync(d_in, in64, 64 * n, cudaMemcpyHostToDevice, s));
-    if (total) CKC(cudaMemcpyAsync(d_msgs, msgs, total, cudaMemcpyHostToDevice, s));
-    CKC(cudaMemcpyAsync(d_off, msg_off, 8 * (n + 1), cudaMemcpyHostToDevice, s));
-    if (sign) {
-        CKC(launch_ed25519_sign(d_out, d_in, d_msgs, d_off, 0, n, g_comb_table_dev, s));
-    } else {
-        CKC(cudaMalloc(&d_pk, 32 * n));
-        CKC(cudaMemcpyAsync(d_pk, pk32, 32 * n, cudaMemcpyHostToDevice, s));
-        CKC(launch_ed25519_verify(reinterpret_cast<int32_t*>(d_out), d_in, d_pk, d_msgs, d_off, 0, n, g_comb_table_dev, s));
-    }
-    CKC(cudaMemcpyAsync(out, d_out, out_rec * n, cudaMemcpyDeviceToHost, s));
-    CKC(cudaStreamSynchronize(s));
-#undef CKC
-    cleanup();
-    return 0;
+    auto body = [&]() -> int {
+        int s = 0;
+        for (size_t base = 0; base < n; s = (s + 1) % kStages) {
+            size_t cnt = 1;
+            while (base + cnt < n && cnt < kChunkOps && msg_off[base + cnt + 1] - msg_off[base] <= kRaggedSliceBytes) cnt++;
+            if (msg_off[base + cnt] < msg_off[base]) return fail(C25519_E_BAD_ARGUMENT, "msg_off must be non-decreasing");
+            const size_t bytes = (size_t)(msg_off[base + cnt] - msg_off[base]);
+            const size_t o_out = 0, o_in = o_out + align_up(out_rec * cnt, 256), o_pk = o_in + align_up(64 * cnt, 256),
+                         o_off = o_pk + align_up(32 * cnt, 256), o_msg = o_off + align_up(8 * (cnt + 1), 256),
+                         total = o_msg + align_up(bytes ? bytes : 1, 256);
+            Stage& st = P->st[s];
+            if (int rc = reserve(st, total)) return rc;
+            st.used = std::max(st.used, total);
+            uint8_t* b = st.dev;
+            CK(cudaMemcpyAsync(b + o_in, in64 + 64 * base, 64 * cnt, cudaMemcpyHostToDevice, st.stream));
+            if (!sign) CK(cudaMemcpyAsync(b + o_pk, pk32 + 32 * base, 32 * cnt, cudaMemcpyHostToDevice, st.stream));
+            CK(cudaMemcpyAsync(b + o_off, msg_off + base, 8 * (cnt + 1), cudaMemcpyHostToDevice, st.stream));
+            if (bytes) CK(cudaMemcpyAsync(b + o_msg, msgs + msg_off[base], bytes, cudaMemcpyHostToDevice, st.stream));
+            const uint8_t* vmsgs = b + o_msg - msg_off[base];       // kernels add the absolute offsets back
+            const uint64_t* d_off = reinterpret_cast<const uint64_t*>(b + o_off);
+            if (sign) CK(launch_ed25519_sign(b + o_out, b + o_in, vmsgs, d_off, 0, cnt, D.comb, st.stream));
+            else CK(launch_ed25519_verify(reinterpret_cast<int32_t*>(b + o_out), b + o_in, b + o_pk, vmsgs, d_off, 0, cnt, D.comb, st.stream));
+            CK(cudaMemcpyAsync(out + out_rec * base, b + o_out, out_rec * cnt, cudaMemcpyDeviceToHost, st.stream));
+            base += cnt;
+        }
+        return 0;
+    };
+    int rc = body();
+    char saved[sizeof t_err]; memcpy(saved, t_err, sizeof saved);
+    int rc2 = drain(P, sign);
+    if (rc) memcpy(t_err, saved, sizeof saved);
+    release(D, P);
+    return rc ? rc : rc2;
 }
 
 int c25519_ed25519_sign_host(uint8_t* sig64, const uint8_t* priv64, const uint8_t* msgs, const uint64_t* msg_off, size_t fixed_len, size_t n)
@@ -401,7 +773,7 @@ int c25519_ed25519_verify_host(int32_t* ok, const uint8_t* sig64, const uint8_t*
     return ed25519_host_msgs(false, reinterpret_cast<uint8_t*>(ok), sig64, pk32, msgs, msg_off, fixed_len, n);
 }
 
-// ------------------------------------------------------------------ the reference's 11-function API (n = 1)
+// ------------------------------------------------------------------ the reference's C API (n = 1)
 static void die_if(int rc, const char* fn)
 {
     if (rc == 0) return;
@@ -413,13 +785,17 @@ static void die_if(int rc, const char* fn)
 void ecp_TrimSecretKey(unsigned char* sk) { sk[0] &= 0xf8; sk[31] = (unsigned char)((sk[31] | 0x40) & 0x7f); }
 
 // Generic k*P exported by the reference's library (source/curve25519_mehdi.h:93) and used by its self-test:
-// K is `len` little-endian bytes (len <= 32), not clamped, not modified.
+// K is `len` little-endian bytes, not clamped, not modified.  The reference walks all `len` bytes; scalars wider than
+// 256 bits have no batched representation here, so non-zero bytes beyond the 32nd are refused loudly, not truncated.
 void ecp_PointMultiply(unsigned char* Q, const unsigned char* P, const unsigned char* K, int len)
 {
     unsigned char k[32] = {0};
+    for (int i = 32; i < len; i++)
+        if (K[i]) { snprintf(t_err, sizeof t_err, "scalar wider than 256 bits (len = %d)", len); die_if(C25519_E_BAD_ARGUMENT, "ecp_PointMultiply"); }
     if (len > 32) len = 32;
     if (len > 0) memcpy(k, K, (size_t)len);
     die_if(c25519_x25519_scalarmult_raw_host(Q, P, k, 1), "ecp_PointMultiply");
+    memset(k, 0, sizeof k);
 }
 
 void curve25519_dh_CalculatePublicKey(unsigned char* pk, unsigned char* sk)
@@ -436,6 +812,7 @@ void ed25519_CreateKeyPair(unsigned char* pubKey, unsigned char* privKey, const 
     (void)blinding;
     unsigned char seed[32]; memcpy(seed, sk, 32);     // privKey may alias sk in caller code
     die_if(c25519_ed25519_keypair_host(pubKey, privKey, seed, 1), "ed25519_CreateKeyPair");
+    memset(seed, 0, sizeof seed);
 }
 
 void ed25519_SignMessage(unsigned char* signature, const unsigned char* privKey, const void* blinding, const unsigned char* msg, size_t msg_size)
@@ -467,58 +844,65 @@ int ed25519_VerifySignature(const unsigned char* signature, const unsigned char*
 }
 
 // Two-phase verification, n = 1: the context is the 2080-byte device-format table copied back to the host.
+static int verify_init_one(uint8_t* ctx, const unsigned char* publicKey)
+{
+    int dev = 0;
+    if (int rc = default_device(&dev)) return rc;
+    DeviceGuard g(dev);
+    Device& D = g_dev[dev];
+    Pipeline* P = acquire(D);
+    if (!P) return fail(C25519_E_OUT_OF_MEMORY, "cannot create pipeline streams");
+    Stage& st = P->st[0];
+    int rc = reserve(st, 4096);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(st.dev + 2304, publicKey, 32, cudaMemcpyHostToDevice, st.stream);
+        if (e == cudaSuccess) e = launch_ed25519_verify_init(st.dev, st.dev + 2304, 1, st.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx, st.dev, C25519_VERIFY_CTX_BYTES, cudaMemcpyDeviceToHost, st.stream);
+        cudaError_t e2 = cudaStreamSynchronize(st.stream);
+        if (e == cudaSuccess) e = e2;
+        if (e != cudaSuccess) rc = fail((int)e, "ed25519_Verify_Init");
+    }
+    release(D, P);
+    return rc;
+}
 void* ed25519_Verify_Init(void* context, const unsigned char* publicKey)
 {
     uint8_t* ctx = static_cast<uint8_t*>(context);
     if (!ctx) ctx = static_cast<uint8_t*>(malloc(C25519_VERIFY_CTX_BYTES));
     if (!ctx) return nullptr;
-    int rc;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        rc = ensure_init_locked();
-        if (!rc) {
-            cudaSetDevice(g_device);
-            Stage& st = g_stage[0];
-            rc = reserve(st, 4096);
-            if (!rc) {
-                cudaError_t e = cudaMemcpyAsync(st.dev + 2304, publicKey, 32, cudaMemcpyHostToDevice, st.stream);
-                if (e == cudaSuccess) e = launch_ed25519_verify_init(st.dev, st.dev + 2304, 1, st.stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx, st.dev, C25519_VERIFY_CTX_BYTES, cudaMemcpyDeviceToHost, st.stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(st.stream);
-                if (e != cudaSuccess) rc = fail((int)e, "ed25519_Verify_Init");
-            }
-        }
-    }
-    die_if(rc, "ed25519_Verify_Init");
+    die_if(verify_init_one(ctx, publicKey), "ed25519_Verify_Init");
     return ctx;
 }
 
+static int verify_check_one(int32_t* ok, const void* context, const unsigned char* signature, const unsigned char* msg, size_t msg_size)
+{
+    int dev = 0;
+    if (int rc = default_device(&dev)) return rc;
+    DeviceGuard g(dev);
+    Device& D = g_dev[dev];
+    Pipeline* P = acquire(D);
+    if (!P) return fail(C25519_E_OUT_OF_MEMORY, "cannot create pipeline streams");
+    Stage& st = P->st[0];
+    int rc = reserve(st, 4096 + align_up(msg_size + 1, 256));
+    if (!rc) {
+        uint8_t* d_ctx = st.dev; uint8_t* d_sig = st.dev + 2304; int32_t* d_ok = reinterpret_cast<int32_t*>(st.dev + 2304 + 64);
+        uint8_t* d_msg = st.dev + 4096;
+        cudaError_t e = cudaMemcpyAsync(d_ctx, context, C25519_VERIFY_CTX_BYTES, cudaMemcpyHostToDevice, st.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_sig, signature, 64, cudaMemcpyHostToDevice, st.stream);
+        if (e == cudaSuccess && msg_size) e = cudaMemcpyAsync(d_msg, msg, msg_size, cudaMemcpyHostToDevice, st.stream);
+        if (e == cudaSuccess) e = launch_ed25519_verify_check(d_ok, d_ctx, nullptr, d_sig, d_msg, nullptr, msg_size, 1, D.comb, st.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ok, d_ok, 4, cudaMemcpyDeviceToHost, st.stream);
+        cudaError_t e2 = cudaStreamSynchronize(st.stream);
+        if (e == cudaSuccess) e = e2;
+        if (e != cudaSuccess) rc = fail((int)e, "ed25519_Verify_Check");
+    }
+    release(D, P);
+    return rc;
+}
 int ed25519_Verify_Check(const void* context, const unsigned char* signature, const unsigned char* msg, size_t msg_size)
 {
     int32_t ok = 0;
-    int rc;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        rc = ensure_init_locked();
-        if (!rc) {
-            cudaSetDevice(g_device);
-            Stage& st = g_stage[0];
-            const size_t need = 4096 + align_up(msg_size + 1, 256);
-            rc = reserve(st, need);
-            if (!rc) {
-                uint8_t* d_ctx = st.dev; uint8_t* d_sig = st.dev + 2304; int32_t* d_ok = reinterpret_cast<int32_t*>(st.dev + 2304 + 64);
-                uint8_t* d_msg = st.dev + 4096;
-                cudaError_t e = cudaMemcpyAsync(d_ctx, context, C25519_VERIFY_CTX_BYTES, cudaMemcpyHostToDevice, st.stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(d_sig, signature, 64, cudaMemcpyHostToDevice, st.stream);
-                if (e == cudaSuccess && msg_size) e = cudaMemcpyAsync(d_msg, msg, msg_size, cudaMemcpyHostToDevice, st.stream);
-                if (e == cudaSuccess) e = launch_ed25519_verify_check(d_ok, d_ctx, nullptr, d_sig, d_msg, nullptr, msg_size, 1, g_comb_table_dev, st.stream);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(&ok, d_ok, 4, cudaMemcpyDeviceToHost, st.stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(st.stream);
-                if (e != cudaSuccess) rc = fail((int)e, "ed25519_Verify_Check");
-            }
-        }
-    }
-    die_if(rc, "ed25519_Verify_Check");
+    die_if(verify_check_one(&ok, context, signature, msg, msg_size), "ed25519_Verify_Check");
     return ok;
 }
 

@@ -64,12 +64,34 @@ C25519_DEV void mad_row(u32* lo, u32* hi, u32 xe0, u32 xe1, u32 xe2, u32 xe3, u3
         : "r"(xo0), "r"(xo1), "r"(xo2), "r"(xo3), "r"(xe0), "r"(xe1), "r"(xe2), "r"(xe3), "r"(y));
 }
 
+// x * 19 for small x.  The multiply pipe is the bound of every kernel here, so with C25519_ALU_SMALL_MUL the product is
+// built from two shift-adds on the ALU pipe instead of an IMAD.
+C25519_DEV u32 mul19(u32 x)
+{
+#ifdef C25519_ALU_SMALL_MUL
+    u32 t, r;
+    asm("{ .reg .u32 s; shl.b32 s, %2, 1; add.u32 %0, s, %2; shl.b32 s, %2, 4; add.u32 %1, s, %0; }" : "=&r"(t), "=r"(r) : "r"(x));
+    return r;
+#else
+    return x * 19u;
+#endif
+}
+// c * 38 for c in {0, 1}
+C25519_DEV u32 bit38(u32 c)
+{
+#ifdef C25519_ALU_SMALL_MUL
+    return (0u - c) & 38u;
+#else
+    return c * 38u;
+#endif
+}
+
 // Final fold of a 9-word value Z[0..7] + w8 * 2^256 (w8 < 2^20) at bit 255:
 //   hi = (w8 << 1) | (Z7 >> 31);  Z = (Z mod 2^255) + 19 * hi          -> N  (no carry out possible)
 C25519_DEV void fold9(u32* z, u32 w8)
 {
     u32 hi = (w8 << 1) | (z[7] >> 31);
-    u32 m = hi * 19u;
+    u32 m = mul19(hi);
     z[7] &= 0x7fffffffu;
     asm("add.cc.u32 %0, %0, %8;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
@@ -465,7 +487,7 @@ C25519_DEV void fe_add(fe& z, const fe& x, const fe& y)
         : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(c)
         : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
           "r"(y.v[0]), "r"(y.v[1]), "r"(y.v[2]), "r"(y.v[3]), "r"(y.v[4]), "r"(y.v[5]), "r"(y.v[6]), "r"(y.v[7]));
-    u32 m = c * 38u, c2;
+    u32 m = bit38(c), c2;
     asm("add.cc.u32  %0, %0, %9;\n\t"
         "addc.cc.u32 %1, %1, 0;\n\t"
         "addc.cc.u32 %2, %2, 0;\n\t"
@@ -477,7 +499,7 @@ C25519_DEV void fe_add(fe& z, const fe& x, const fe& y)
         "addc.u32    %8, 0, 0;"
         : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "=&r"(c2)
         : "r"(m));
-    t[0] += c2 * 38u;                   // a second wrap leaves t < 38, so this cannot carry
+    t[0] += bit38(c2);                  // a second wrap leaves t < 38, so this cannot carry
 #pragma unroll
     for (int i = 0; i < 8; i++) z.v[i] = t[i];
 }
@@ -499,7 +521,7 @@ C25519_DEV void fe_add_nn(fe& z, const fe& x, const fe& y)
         : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(c)
         : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
           "r"(y.v[0]), "r"(y.v[1]), "r"(y.v[2]), "r"(y.v[3]), "r"(y.v[4]), "r"(y.v[5]), "r"(y.v[6]), "r"(y.v[7]));
-    t[0] += c * 38u;
+    t[0] += bit38(c);
 #pragma unroll
     for (int i = 0; i < 8; i++) z.v[i] = t[i];
 }

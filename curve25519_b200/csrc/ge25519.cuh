@@ -53,7 +53,10 @@ C25519_DEV void ge_double(ge_ext& p)
     if (WITH_T) fe_mul(p.t, e, s);
 }
 
-// shared tail of the two additions: given A, B, C (N) and D = 2 Z1 Z2 (W or N)
+// shared tail of the two additions: given A, B, C (N) and D = 2 Z1 Z2 (W or N).
+// WITH_T = false skips T3 = E H: an addition whose result is only ever doubled next (the doubling does not read T) or
+// encoded does not need it; X, Y, Z -- and therefore every later point -- are unchanged.
+template <bool WITH_T = true>
 C25519_DEV void ge_add_tail(ge_ext& r, const fe& a, const fe& b, const fe& c, const fe& d, bool d_is_narrow)
 {
     fe e, h, f, g;
@@ -63,11 +66,12 @@ C25519_DEV void ge_add_tail(ge_ext& r, const fe& a, const fe& b, const fe& c, co
     if (d_is_narrow) fe_add_nn(g, d, c); else fe_add(g, d, c);   // G = D + C
     fe_mul(r.x, e, f);
     fe_mul(r.y, h, g);
-    fe_mul(r.t, e, h);
+    if (WITH_T) fe_mul(r.t, e, h);
     fe_mul(r.z, g, f);
 }
 
-// P <- P + Q, Q precomputed affine (Z2 = 1).   7M.
+// P <- P + Q, Q precomputed affine (Z2 = 1).   7M (6M without T).
+template <bool WITH_T = true>
 C25519_DEV void ge_add_affine(ge_ext& p, const ge_pa& q)
 {
     fe a, b, c, d;
@@ -77,10 +81,11 @@ C25519_DEV void ge_add_affine(ge_ext& p, const ge_pa& q)
     fe_mul(b, b, q.ypx);
     fe_mul(c, p.t, q.t2d);
     fe_add_nn(d, p.z, p.z);         // D = 2 Z1      W
-    ge_add_tail(p, a, b, c, d, false);
+    ge_add_tail<WITH_T>(p, a, b, c, d, false);
 }
 
-// R <- P + Q, Q precomputed projective.   8M.   (R may alias P)
+// R <- P + Q, Q precomputed projective.   8M (7M without T).   (R may alias P)
+template <bool WITH_T = true>
 C25519_DEV void ge_add_pe(ge_ext& r, const ge_ext& p, const ge_pe& q)
 {
     fe a, b, c, d;
@@ -90,7 +95,7 @@ C25519_DEV void ge_add_pe(ge_ext& r, const ge_ext& p, const ge_pe& q)
     fe_mul(b, b, q.ypx);
     fe_mul(c, p.t, q.t2d);
     fe_mul(d, p.z, q.z2);           // D = Z1 * 2 Z2  N
-    ge_add_tail(r, a, b, c, d, true);
+    ge_add_tail<WITH_T>(r, a, b, c, d, true);
 }
 
 // Ext -> PE.   1M.   p coordinates N.
@@ -158,6 +163,7 @@ C25519_DEV void comb_load(ge_pa& q, const u32* __restrict__ table_smem, u32 idx)
 
 // S <- a * B by the 8-fold comb: 32 table look-ups, 31 doublings, 31 affine additions
 // (edp_BasePointMult with the Z-randomiser taken as 1: the start point is (2x, 2y, 2, 2xy)).
+// On return S.t is stale (never needed: every caller encodes or normalises X, Y, Z).
 C25519_DEV void ge_base_comb(ge_ext& S, const u32 (&a)[8], const u32* __restrict__ table_smem)
 {
     ge_pa q;
@@ -174,7 +180,7 @@ C25519_DEV void ge_base_comb(ge_ext& S, const u32 (&a)[8], const u32* __restrict
     for (int i = 1; i < 32; i++) {
         ge_double(S);
         comb_load(q, table_smem, comb8_index(a, i));
-        ge_add_affine(S, q);
+        ge_add_affine<false>(S, q);         // next: a doubling or the end -- T is never read again
     }
 }
 

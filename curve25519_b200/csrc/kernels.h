@@ -13,9 +13,6 @@ constexpr int kCombWordsPerEntry = 24;
 constexpr int kCombTableBytes = kCombEntries * kCombWordsPerEntry * 4;   // 24 576
 constexpr int kCombStrideWordsHost = 28;   // padded device/shared-memory stride (== kCombStrideWords in ge25519.cuh)
 
-// device copy of the comb table (global memory; staged into shared memory per CTA by TMA bulk copy)
-extern const uint32_t* g_comb_table_dev;
-
 cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s);
 cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, cudaStream_t s);
 cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
@@ -38,9 +35,18 @@ cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size
 // below this many operations a batch is latency-bound and each kernel does its own inversion (one launch)
 constexpr size_t kDeferThreshold = 256;
 
+cudaError_t launch_modl(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n, cudaStream_t s);
 cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s);
 cudaError_t launch_imad_peak(uint64_t* mac_per_launch, uint32_t* sink, int iters, cudaStream_t s);
 
 void count_launch();
+
+// zeroise a stream-ordered scratch buffer that held secret-derived data, then return it to the pool
+inline cudaError_t wipe_and_free(void* p, size_t bytes, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, s);
+    cudaError_t e2 = cudaFreeAsync(p, s);
+    return e != cudaSuccess ? e : e2;
+}
 
 }  // namespace c25519

@@ -86,14 +86,13 @@ cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// IMAD.WIDE.U32 rate of this device, measured two ways (SASS of both loops checked with cuobjdump):
-//   form 0 "fresh"      : IMAD.WIDE.U32 Rd, Ra, Rb, RZ        (2 register reads)  -- the fastest form that exists;
-//                         this is the conservative roofline denominator bench.py reports against.
-//   form 1 "accumulate" : IMAD.WIDE.U32 Rd, Ra, Rb, Rd        (4 register reads: 64-bit accumulator)  -- the form a
-//                         multi-precision multiply-accumulate needs for ~3/4 of its products; measured at ~0.56x the
-//                         fresh rate on B200 (see profiles/r1_ubench4.txt), so it is the practical bound of fe_mul.
-// 8 independent products per loop trip, distinct operands (no operand-reuse cache hits), no memory traffic.
-// 148 SMs x 4 resident CTAs x 256 threads.
+// IMAD.WIDE.U32 rate of this device, measured two ways.  tests/test_sass.py disassembles the built object and
+// asserts that each loop body really holds eight IMAD.WIDE.U32 of the stated form (round 1's "fresh" loop let ptxas
+// hoist seven of its eight products):
+//   form 0 "fresh"      : IMAD.WIDE.U32 Rd, Ra, Rb, RZ   -- every product fed back into its own multiplicand
+//   form 1 "accumulate" : IMAD.WIDE.U32 Rd, Ra, Rb, Rd   -- 64-bit register accumulator, the form a multi-precision
+//                         multiply-accumulate uses for most of its products
+// 8 independent chains per loop trip, no memory traffic, 148 SMs x 4 resident CTAs x 256 threads.
 constexpr int kPeakBlocks = 148 * 4;
 constexpr int kPeakThreads = 256;
 
@@ -108,7 +107,6 @@ k_imad_peak(uint32_t* sink, const uint32_t* src, int iters)
         x4 = src[(t + 12) & 63] | 1, x5 = src[(t + 13) & 63] | 1, x6 = src[(t + 14) & 63] | 1, x7 = src[(t + 15) & 63] | 1;
     u32 y0 = src[(t + 16) & 63] | 1, y1 = src[(t + 17) & 63] | 1, y2 = src[(t + 18) & 63] | 1, y3 = src[(t + 19) & 63] | 1,
         y4 = src[(t + 20) & 63] | 1, y5 = src[(t + 21) & 63] | 1, y6 = src[(t + 22) & 63] | 1, y7 = src[(t + 23) & 63] | 1;
-    u32 r0 = x0, r1 = x1, r2 = x2, r3 = x3, r4 = x4, r5 = x5, r6 = x6, r7 = x7;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
         unsigned long long p0, p1, p2, p3, p4, p5, p6, p7;
@@ -117,16 +115,18 @@ k_imad_peak(uint32_t* sink, const uint32_t* src, int iters)
                      : "=l"(p0), "=l"(p1), "=l"(p2), "=l"(p3), "=l"(p4), "=l"(p5), "=l"(p6), "=l"(p7)
                      : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6), "r"(x7),
                        "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(y4), "r"(y5), "r"(y6), "r"(y7));
-        if (FORM == 0) {        // consume the fresh products on the ALU pipe (one 3-input XOR each)
-            r0 ^= (u32)p0 ^ (u32)(p0 >> 32); r1 ^= (u32)p1 ^ (u32)(p1 >> 32); r2 ^= (u32)p2 ^ (u32)(p2 >> 32); r3 ^= (u32)p3 ^ (u32)(p3 >> 32);
-            r4 ^= (u32)p4 ^ (u32)(p4 >> 32); r5 ^= (u32)p5 ^ (u32)(p5 >> 32); r6 ^= (u32)p6 ^ (u32)(p6 >> 32); r7 ^= (u32)p7 ^ (u32)(p7 >> 32);
-        } else {                // ptxas folds these 64-bit adds into the multiply: IMAD.WIDE.U32 Rd, Ra, Rb, Rd
+        if (FORM == 0) {        // every chain feeds its product back into its own multiplicand (one 3-input XOR on the ALU pipe
+                                // each), so all eight products are loop-variant: nothing can be hoisted out of the loop
+            x0 ^= (u32)p0 ^ (u32)(p0 >> 32); x1 ^= (u32)p1 ^ (u32)(p1 >> 32); x2 ^= (u32)p2 ^ (u32)(p2 >> 32); x3 ^= (u32)p3 ^ (u32)(p3 >> 32);
+            x4 ^= (u32)p4 ^ (u32)(p4 >> 32); x5 ^= (u32)p5 ^ (u32)(p5 >> 32); x6 ^= (u32)p6 ^ (u32)(p6 >> 32); x7 ^= (u32)p7 ^ (u32)(p7 >> 32);
+        } else {                // ptxas folds these 64-bit adds into the multiply: IMAD.WIDE.U32 Rd, Ra, Rb, Rd.  The accumulators
+                                // change every trip, so the multiply-adds cannot be hoisted even where x_k, y_k are loop-invariant.
             a0 += p0; a1 += p1; a2 += p2; a3 += p3; a4 += p4; a5 += p5; a6 += p6; a7 += p7;
         }
-        x0 += 1;                // keeps the products loop-variant
+        if (FORM != 0) x0 += 1;
     }
     unsigned long long r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-    u32 q = r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7 ^ x0;
+    u32 q = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
     if ((u32)r == 0x12345u && q == 77u) sink[0] = (u32)(r >> 32);      // never true in practice; keeps the chains alive
 }
 

@@ -5,8 +5,9 @@
 //
 // Same algorithm shape as the reference (start from the top set bit with P = (u:1), Q = 2P, then one
 // "P <- P+Q, Q <- 2Q" step per remaining bit with the roles of P and Q chosen by the bit), with the
-// reference's pointer-table operand selection (ECP_MONT :89) replaced by a lane-uniform conditional
-// register swap, and its projective-Z randomisation (:123) dropped (result-neutral).
+// reference's pointer-table operand selection (ECP_MONT :89) replaced by a branch-free select of the point
+// that gets doubled (the differential addition is symmetric), and its projective-Z randomisation (:123)
+// dropped (result-neutral).
 // All 256 bits of u are used (no bit-255 masking, :104); Z = 0 at the end gives 32 zero bytes (:148-150).
 #pragma once
 #include "fe25519.cuh"
@@ -52,6 +53,34 @@ C25519_DEV void mont_step_with(fe& SX, fe& SZ, fe& DX, fe& DZ, BaseLoader load_b
     fe_mul(DZ, A, B);
 }
 
+// The same step with the conditional swap folded in: the differential addition is symmetric in its two inputs, so only
+// the DOUBLING has to know which point it doubles -- `dbl_s` selects the S slot instead of the D slot (what a full
+// cswap(S, D) before mont_step_with would achieve) with 16 limb selects on the sum/difference pair instead of 32 swaps.
+template <typename BaseLoader>
+C25519_DEV void mont_step_sel(fe& SX, fe& SZ, fe& DX, fe& DZ, bool dbl_s, BaseLoader load_base)
+{
+    fe A, B, C, D, P, M;
+    fe_sub(A, SX, SZ);
+    fe_add_nn(B, SX, SZ);
+    fe_sub(C, DX, DZ);
+    fe_add_nn(D, DX, DZ);
+    fe_select(P, D, B, dbl_s);          // x + z of the point to double
+    fe_select(M, C, A, dbl_s);          // x - z
+    fe_mul(A, A, D);
+    fe_mul(B, B, C);
+    fe_add_nn(SX, A, B);
+    fe_sub(B, A, B);
+    fe_sqr(SX, SX);
+    fe_sqr(A, B);
+    { fe base; load_base(base); fe_mul(SZ, A, base); }
+    fe_sqr(A, P);
+    fe_sqr(B, M);
+    fe_mul(DX, A, B);
+    fe_sub(B, A, B);
+    fe_mul_small_add(A, A, 121665u, B);
+    fe_mul(DZ, A, B);
+}
+
 C25519_DEV void mont_step(fe& SX, fe& SZ, fe& DX, fe& DZ, const fe& base)
 { mont_step_with(SX, SZ, DX, DZ, [&](fe& b) { fe_copy(b, base); }); }
 
@@ -76,10 +105,14 @@ C25519_DEV void x25519_ladder_projective(fe& PX, fe& PZ, const fe& u, KeyWord kw
     for (int bit = 253; bit >= 0; --bit) {
         bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
         bool s = (b != cur);
+        cur = b;
+#ifdef C25519_LADDER_CSWAP           // round-1 form: physical swap of the two slots, 0.75 % slower (profiles/r2_ladder_lab2.txt)
         fe_cswap(R0X, R1X, s);
         fe_cswap(R0Z, R1Z, s);
-        cur = b;
         mont_step(R0X, R0Z, R1X, R1Z, u);    // bit = 1: P += Q, Q = 2Q ; bit = 0: Q += P, P = 2P
+#else
+        mont_step_sel(R0X, R0Z, R1X, R1Z, s, [&](fe& bb) { fe_copy(bb, u); });
+#endif
     }
     fe_select(PX, R1X, R0X, cur);
     fe_select(PZ, R1Z, R0Z, cur);
@@ -103,10 +136,8 @@ C25519_DEV void x25519_ladder_projective_raw(fe& PX, fe& PZ, const fe& u, KeyWor
     for (int bit = 255; bit >= 0; --bit) {
         bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
         bool s = (b != cur);
-        fe_cswap(R0X, R1X, s);
-        fe_cswap(R0Z, R1Z, s);
         cur = b;
-        mont_step(R0X, R0Z, R1X, R1Z, u);
+        mont_step_sel(R0X, R0Z, R1X, R1Z, s, [&](fe& bb) { fe_copy(bb, u); });
     }
     fe_select(PX, R1X, R0X, cur);
     fe_select(PZ, R1Z, R0Z, cur);

@@ -82,7 +82,7 @@ cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, con
     count_launch();
     e = cudaGetLastError();
     if (e == cudaSuccess) e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s);
-    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    cudaError_t e2 = wipe_and_free(scratch, n * kScratchXZ, s);
     return e != cudaSuccess ? e : e2;
 }
 
@@ -114,7 +114,7 @@ cudaError_t launch_x25519_shared_kdf(uint8_t* key_out, unsigned key_size, const 
         count_launch();
         e = cudaGetLastError();
     }
-    cudaError_t e2 = cudaFreeAsync(secret, s);
+    cudaError_t e2 = wipe_and_free(secret, n * 32, s);
     return e != cudaSuccess ? e : e2;
 }
 
@@ -159,7 +159,7 @@ cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, in
         count_launch();
         e = cudaGetLastError();
     }
-    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    cudaError_t e2 = wipe_and_free(scratch, n_local * kScratchXZ, s);
     return e != cudaSuccess ? e : e2;
 }
 
@@ -195,7 +195,7 @@ cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, ui
     count_launch();
     e = cudaGetLastError();
     if (e == cudaSuccess) e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s);
-    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    cudaError_t e2 = wipe_and_free(scratch, n * kScratchXZ, s);
     return e != cudaSuccess ? e : e2;
 }
 

@@ -79,3 +79,13 @@ P_FIELD = 2**255 - 19
 # dh_test secret keys = SHA-256("1234"), SHA-256("abcd") (test/curve25519_test.c:435-445)
 DH_TEST["alice_sk"] = "03ac674216f3e15c761ee1a5e255f067953623c8b388b4459e13f978d7c846f4"
 DH_TEST["bruce_sk"] = "88d4266fd4e6338d13b845fcf289579d209c897823b9217da3e161936f031589"
+
+# ---- the reference self-test's own constants (test/curve25519_selftest.c), memory byte order
+SELFTEST_PK1 = "46f9d209c75369ac5f97a328a1667ac7f86d5ec9b20d515c1139a2563b101360"     # :109-111 (used as a raw scalar)
+SELFTEST_PK2 = "5a266ad3d08d9e9b8bd92acccd87d5b996d1dbbab6bcc9756276d761f9375fa7"     # :113-115
+SELFTEST_K1 = "0be3be63bc016aaac9e5279fb790fb44372b2d4da1735b5bb01ac0318d892103"      # :101-103, k1 * k2 == 1 mod L
+SELFTEST_K2 = "3903e3277e4193612d3d40193d606821602 5ef90b98b24f250609421d4743605".replace(" ", "")   # :105-107
+# I * D mod BPO (:128-129), little-endian bytes of W256(0xFDC0315D, ..., 0x00A63CC5)
+SELFTEST_IXD_MOD_BPO = "5d31c0fd60f48e59f44916e17ceeeb2db4ef7802fe771833ce3ee0fbc53ca600"
+CONST_I = 0x2b8324804fc1df0b2b4d00993dfbd7a72f431806ad2fe478c4ee1b274a0ea0b0      # sqrt(-1) mod p
+CONST_D = 0x52036cee2b6ffe738cc740797779e89800700a4d4141d8ab75eb4dca135978a3      # Edwards d
