@@ -20,6 +20,14 @@
 namespace c25519 {
 
 constexpr int kThreads = 128;
+// resident CTAs per SM the verification kernels are compiled for (register budget = 65536 / (128 x this)); measured in
+// tools/verify_lab.cu, profiles/r2_verify_lab.txt
+#ifndef C25519_VERIFY_INIT_MINB
+#define C25519_VERIFY_INIT_MINB 4
+#endif
+#ifndef C25519_VERIFY_CHECK_MINB
+#define C25519_VERIFY_CHECK_MINB 4
+#endif
 constexpr int kCombSmemWords = kCombEntries * kCombStrideWords;       // 7168 words = 28 672 B
 constexpr int kCtxBytes = 2080;
 static_assert(kCombStrideWords == kCombStrideWordsHost, "comb table stride mismatch between host image and kernels");
@@ -220,7 +228,7 @@ C25519_DEV void load_pe(ge_pe& q, const uint8_t* p)        // 128-byte table ent
 }
 
 // ctx record: [0,32) public key bytes, [32 + 128 j, 32 + 128 (j+1)) table entry j = sum_{k in bits(j)} 2^(64k) (-A)
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, C25519_VERIFY_INIT_MINB)
 k_ed25519_verify_init(uint8_t* __restrict__ ctx, const uint8_t* __restrict__ pk32, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -268,7 +276,7 @@ k_ed25519_verify_init(uint8_t* __restrict__ ctx, const uint8_t* __restrict__ pk3
 }
 
 template <bool DEFER>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, C25519_VERIFY_CHECK_MINB)
 k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx, const uint32_t* __restrict__ key_index,
                        const uint8_t* __restrict__ sig64, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ off,
                        size_t fixed_len, size_t n, const u32* __restrict__ gtable, uint8_t* __restrict__ scratch)

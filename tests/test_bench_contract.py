@@ -25,6 +25,17 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    v = d["ed25519_verify"]                     # the second headline of BASELINE.json's metric, same arm
+    assert v["metric"] == "ed25519_verify_ops_per_sec" and v["value"] > 0 and v["cpu_baseline"]["cores"] >= 1
+
+
+def test_reference_arm_verify_metric():
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--metric", "ed25519_verify", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["metric"] == "ed25519_verify_ops_per_sec" and d["value"] > 0 and d["x25519_shared"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_are_silent():
