@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libcurve25519_b200.so")
-UNITS = ["engine.cu", "x25519_kernels.cu", "ed25519_kernels.cu", "modl_kernels.cu", "test_kernels.cu", "comb_table.cu"]
+UNITS = ["engine.cu", "x25519_kernels.cu", "ed25519_kernels.cu", "modl_kernels.cu", "legacy_internals.cu", "test_kernels.cu", "comb_table.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall", "--expt-relaxed-constexpr"]

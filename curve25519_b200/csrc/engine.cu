@@ -29,7 +29,7 @@
 
 namespace c25519 {
 
-extern const uint32_t kCombTableHost[kCombEntries * kCombWordsPerEntry];   // comb_table.cu (generated)
+extern const uint32_t (&kCombTableHost)[kCombEntries * kCombWordsPerEntry];   // comb_table.cu (generated)
 
 namespace {
 
@@ -354,6 +354,38 @@ int exchange_rows(uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t 
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// One word-level legacy operation (csrc/legacy_internals.cu) on the default device: `nin` words in, `nout` words out.
+// Like the other n = 1 wrappers it has no error channel: a CUDA failure aborts with a message (no CPU fallback).
+void legacy_run(int op, const uint32_t* in, int nin, uint32_t* out, int nout)
+{
+    int dev = 0, rc = default_device(&dev);
+    if (!rc) {
+        DeviceGuard g(dev);
+        Device& D = g_dev[dev];
+        Pipeline* P = acquire(D);
+        if (!P) rc = fail(C25519_E_OUT_OF_MEMORY, "cannot create pipeline streams");
+        else {
+            Stage& st = P->st[0];
+            rc = reserve(st, align_up(4 * (size_t)(nin + nout), 256));
+            if (!rc) {
+                uint32_t* io = reinterpret_cast<uint32_t*>(st.dev);
+                cudaError_t e = cudaMemcpyAsync(io, in, 4 * (size_t)nin, cudaMemcpyHostToDevice, st.stream);
+                if (e == cudaSuccess) e = launch_legacy_op(op, io, nin, D.comb, st.stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(out, io + nin, 4 * (size_t)nout, cudaMemcpyDeviceToHost, st.stream);
+                if (e == cudaSuccess) e = cudaMemsetAsync(io, 0, 4 * (size_t)(nin + nout), st.stream);     // operands may be secrets
+                cudaError_t e2 = cudaStreamSynchronize(st.stream);
+                if (e == cudaSuccess) e = e2;
+                if (e != cudaSuccess) rc = fail((int)e, "legacy word-level operation");
+            }
+            release(D, P);
+        }
+    }
+    if (rc) {
+        fprintf(stderr, "libcurve25519_b200: legacy operation %d failed (%d): %s -- there is no CPU fallback\n", op, rc, t_err);
+        abort();
+    }
+}
 
 }  // namespace c25519
 

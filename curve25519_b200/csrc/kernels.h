@@ -36,6 +36,7 @@ cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size
 constexpr size_t kDeferThreshold = 256;
 
 cudaError_t launch_modl(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n, cudaStream_t s);
+cudaError_t launch_legacy_op(int op, uint32_t* io, int nin, const uint32_t* table, cudaStream_t s);
 cudaError_t launch_test_primitive(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n, cudaStream_t s);
 cudaError_t launch_imad_peak(uint64_t* mac_per_launch, uint32_t* sink, int iters, cudaStream_t s);
 
