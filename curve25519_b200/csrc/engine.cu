@@ -48,8 +48,8 @@ struct Pipeline { Stage st[kStages]; bool busy = false; };
 struct Device {
     std::atomic<bool> ready{false};
     const uint32_t* comb = nullptr;                 // device image of the comb table (padded stride)
-    cudaStream_t side = nullptr;                    // side stream for the overlapped NCCL exchange
-    cudaEvent_t ev_slice[8] = {}, ev_done = nullptr;
+    cudaStream_t side = nullptr;                    // finish stream: batched inversion + NCCL exchange of a slice
+    cudaStream_t aux = nullptr;                     // second compute stream: odd slices' ladders (no drain bubble between slices)
     std::mutex mu;                                  // guards `pipes`
     std::condition_variable cv;
     std::vector<Pipeline*> pipes;
@@ -109,8 +109,7 @@ int ensure_device(int dev)
     CK(cudaMemcpy(t, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
     d.comb = t;
     CK(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
-    for (auto& ev : d.ev_slice) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&d.ev_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking));
     {   // keep the stream-ordered scratch allocations of the launchers cached in the pool between calls
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -351,6 +350,49 @@ int exchange_rows(uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t 
     return 0;
 }
 
+// X25519 over a large HBM-resident batch, software-pipelined: the batch is cut into `slices`.  Even slices' ladders run on the
+// caller's stream, odd slices' on the device's aux stream (forked from the caller's stream), so the CTAs of slice i+1 start
+// the moment slots free up while slice i drains -- no bubble at the slice boundary.  Slice i's batched inversion
+// (latency-bound: one 265-operation chain per thread) and -- for the sharded entry point -- its NCCL exchange run on the
+// finish stream underneath the later slices' ladders; only the last slice's finish is exposed.  Everything joins the
+// caller's stream again before the call returns.  `after_slice(row0, cnt, finish_stream)` runs once per slice.
+template <typename AfterSlice>
+int x25519_pipelined(Device& D, uint8_t* out32, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, cudaStream_t s,
+                     const size_t* bounds, int slices, AfterSlice after_slice)
+{
+    cudaEvent_t ev[8] = {}, fork = nullptr, done = nullptr, aux_done = nullptr;   // per-call events: callers never share one
+    int rc = 0, made = 0;
+    auto body = [&]() -> int {
+        CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(fork, s));                                 // earlier work on the caller's stream (e.g. the inputs)
+        CK(cudaStreamWaitEvent(D.aux, fork, 0));
+        for (int i = 0; i < slices; i++) {
+            const size_t row0 = bounds[i], cnt = bounds[i + 1] - bounds[i];       // bounds[0] = 0 < ... < bounds[slices] = n
+            if (cnt == 0) continue;
+            cudaStream_t cs = (i & 1) ? D.aux : s;
+            uint8_t* scratch = nullptr;
+            CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming)); made = i + 1;
+            CK(launch_x25519_projective(&scratch, pk32 ? pk32 + 32 * row0 : nullptr, sk32_inout + 32 * row0, cnt, cs));
+            CK(cudaEventRecord(ev[i], cs));
+            CK(cudaStreamWaitEvent(D.side, ev[i], 0));
+            CK(launch_x25519_finish(scratch, out32 + 32 * row0, cnt, D.side));
+            if (int r = after_slice(row0, cnt, D.side)) return r;
+        }
+        CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CK(cudaEventRecord(done, D.side));
+        CK(cudaStreamWaitEvent(s, done, 0));
+        CK(cudaEventCreateWithFlags(&aux_done, cudaEventDisableTiming));
+        CK(cudaEventRecord(aux_done, D.aux));
+        CK(cudaStreamWaitEvent(s, aux_done, 0));
+        return 0;
+    };
+    rc = body();
+    for (int i = 0; i < made; i++) cudaEventDestroy(ev[i]);      // released by the runtime once the recorded work completes
+    for (cudaEvent_t e : {fork, done, aux_done}) if (e) cudaEventDestroy(e);
+    return rc;
+}
+constexpr size_t kPipelineMinOps = (size_t)1 << 18;      // below this a batch is one launch pair (nothing to overlap)
+
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -415,9 +457,8 @@ int c25519_shutdown(void)
             }
             d.pipes.clear();
         }
-        for (auto& ev : d.ev_slice) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
-        if (d.ev_done) { cudaEventDestroy(d.ev_done); d.ev_done = nullptr; }
         if (d.side) { cudaStreamDestroy(d.side); d.side = nullptr; }
+        if (d.aux) { cudaStreamDestroy(d.aux); d.aux = nullptr; }
         cudaFree(const_cast<uint32_t*>(d.comb));
         d.comb = nullptr;
         d.ready.store(false);
@@ -442,6 +483,7 @@ int c25519_x25519_shared_batch(uint8_t* out32, const uint8_t* pk32, uint8_t* sk3
     if (n && (!out32 || !pk32 || !sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     if (misaligned32(out32) || misaligned32(pk32) || misaligned32(sk32_inout)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     BATCH_PROLOGUE(out32, pk32, sk32_inout);
+    // one ladder launch + one batched inversion: slicing a single-GPU batch was measured 0.3 - 1.5 % slower
     CK(launch_x25519_ladder(out32, pk32, sk32_inout, n, (cudaStream_t)stream));
     return 0;
 }
@@ -600,8 +642,8 @@ int c25519_allgather_records(void* all, size_t rec_bytes, size_t n_local, void* 
 }
 
 // X25519 shared keys, sharded: this rank computes rows [rank*n_local, (rank+1)*n_local) of out_all and receives the other
-// ranks' rows.  The local batch is cut into up to four slices; slice i's exchange runs on a side stream underneath slice
-// i+1's ladder, so only the last slice's transfer is exposed.
+// ranks' rows.  The local batch is cut into two slices; the first slice's batched inversion and NCCL exchange run on a side
+// stream underneath the second slice's ladder, so only the last slice's finish + transfer is exposed.
 int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, uint8_t* sk32_local_inout, size_t n_local,
                                  void* nccl_comm, void* stream)
 {
@@ -613,25 +655,18 @@ int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, ui
     BATCH_PROLOGUE(out_all, pk32_local, sk32_local_inout);
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t* mine = out_all + (size_t)rank * n_local * 32;
-    const int slices = world == 1 ? 1 : (n_local >= ((size_t)1 << 18) ? 4 : (n_local >= ((size_t)1 << 16) ? 2 : 1));
-    if (slices == 1) {
+    if (n_local < kPipelineMinOps) {
         CK(launch_x25519_ladder(mine, pk32_local, sk32_local_inout, n_local, s));
         if (world > 1) return exchange_rows(out_all, 32, n_local, 0, n_local, world, rank, nccl_comm, s);
         return 0;
     }
-    const size_t per = (n_local + slices - 1) / slices;
-    for (int i = 0; i < slices; i++) {
-        const size_t row0 = (size_t)i * per;
-        if (row0 >= n_local) break;
-        const size_t cnt = std::min(per, n_local - row0);
-        CK(launch_x25519_ladder(mine + 32 * row0, pk32_local + 32 * row0, sk32_local_inout + 32 * row0, cnt, s));
-        CK(cudaEventRecord(D.ev_slice[i], s));
-        CK(cudaStreamWaitEvent(D.side, D.ev_slice[i], 0));
-        if (int rc = exchange_rows(out_all, 32, n_local, row0, cnt, world, rank, nccl_comm, D.side)) return rc;
-    }
-    CK(cudaEventRecord(D.ev_done, D.side));
-    CK(cudaStreamWaitEvent(s, D.ev_done, 0));
-    return 0;
+    // Two slices, 7/8 + 1/8: the big slice's inversion and exchange (the bulk of the transfer) hide under the small slice's
+    // ladder; only the small slice's finish + an eighth of the transfer are exposed, and there is a single slice boundary.
+    const size_t cut = (n_local - n_local / 8 + 127) & ~(size_t)127;
+    const size_t bounds[3] = {0, cut, n_local};
+    return x25519_pipelined(D, mine, pk32_local, sk32_local_inout, n_local, s, bounds, 2, [&](size_t row0, size_t cnt, cudaStream_t side) -> int {
+        return world > 1 ? exchange_rows(out_all, 32, n_local, row0, cnt, world, rank, nccl_comm, side) : 0;
+    });
 }
 
 int c25519_x25519_public_sharded(uint8_t* pk_all, uint8_t* sk32_local_inout, size_t n_local, int ladder, void* nccl_comm, void* stream)

@@ -14,6 +14,8 @@ constexpr int kCombTableBytes = kCombEntries * kCombWordsPerEntry * 4;   // 24 5
 constexpr int kCombStrideWordsHost = 28;   // padded device/shared-memory stride (== kCombStrideWords in ge25519.cuh)
 
 cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s);
+cudaError_t launch_x25519_projective(uint8_t** scratch_out, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s);
+cudaError_t launch_x25519_finish(uint8_t* scratch, uint8_t* out32, size_t n, cudaStream_t s_finish);
 cudaError_t launch_x25519_ladder_raw(uint8_t* out32, const uint8_t* point32, const uint8_t* scalar32, size_t n, cudaStream_t s);
 cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, int rank, const uint8_t* pk32, uint8_t* sk32_inout,
                                          size_t n_local, cudaStream_t s);

@@ -179,6 +179,30 @@ cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size
     return cudaGetLastError();
 }
 
+// The two halves of a large X25519 batch, separately launchable so that a caller can run the (latency-bound) batched
+// inversion of one slice on a side stream underneath the ladder of the next slice (engine.cu: x25519_pipelined):
+//   launch_x25519_projective : allocate the scratch on `s`, run the ladder, leave (X : Z) records in *scratch_out
+//   launch_x25519_finish     : normalise into out32 on `s_finish` (the caller orders it after the ladder), wipe and free
+cudaError_t launch_x25519_projective(uint8_t** scratch_out, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s)
+{
+    uint8_t* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, n * kScratchXZ, s);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
+    k_x25519_ladder<true><<<grid, kLadderThreads, 0, s>>>(nullptr, pk32_or_null, sk32_inout, n, scratch);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { wipe_and_free(scratch, n * kScratchXZ, s); return e; }
+    *scratch_out = scratch;
+    return cudaSuccess;
+}
+cudaError_t launch_x25519_finish(uint8_t* scratch, uint8_t* out32, size_t n, cudaStream_t s_finish)
+{
+    cudaError_t e = launch_normalize(kNormX, scratch, kScratchXZ, n, out32, 32, nullptr, 0, nullptr, 0, nullptr, s_finish);
+    cudaError_t e2 = wipe_and_free(scratch, n * kScratchXZ, s_finish);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, uint8_t* sk32_inout, size_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;

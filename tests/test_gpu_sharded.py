@@ -23,7 +23,7 @@ def test_single_rank_communicator(engine, oracle, rng):
     import torch
     comm = engine.ShardedComm(1, 0, torch.cuda.current_device(), lambda uid: uid)
     try:
-        n = 70000                                                   # world == 1: one slice, no exchange
+        n = (1 << 18) + 77                                          # world == 1: four pipelined slices, no exchange
         sk = rng.integers(0, 256, (n, 32), dtype=np.uint8); pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
         d_sk = torch.from_numpy(sk).cuda(); d_pk = torch.from_numpy(pk).cuda()
         out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
@@ -63,7 +63,7 @@ def _worker(rank, world, port, n_local, q):
         seed = rng.integers(0, 256, (ne, 32), dtype=np.uint8); msgs = rng.integers(0, 256, (ne, 64), dtype=np.uint8)
         T = max(1, (os.cpu_count() or 2) // world)
         lo, hi = rank * n_local, (rank + 1) * n_local
-        # --- X25519 shared keys: 2 overlapped slices when n_local >= 2^16
+        # --- X25519 shared keys: 4 pipelined slices (inversion + exchange under the next ladder) when n_local >= 2^18
         out_all = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
         d_sk = torch.from_numpy(sk[lo:hi]).cuda()
         api.x25519_shared_sharded(comm, out_all, torch.from_numpy(pk[lo:hi]).cuda(), d_sk)
@@ -115,7 +115,7 @@ def test_config5_gathered_buffers_on_every_rank():
     q = ctx.Queue()
     port = _free_port()
     world = 2
-    ps = [ctx.Process(target=_worker, args=(r, world, port, (1 << 16) + 512, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, (1 << 18) + 512, q)) for r in range(world)]
     [p.start() for p in ps]
     res = [q.get(timeout=600) for _ in ps]
     [p.join(60) for p in ps]
