@@ -287,6 +287,8 @@ class Job:
                       for _ in range(self.nsets)]
             self.d = [{"sk": dev(s["sk"]), "pk": dev(s["pk"]), "out": torch.empty((n, 32), dtype=torch.uint8, device="cuda")} for s in self.h]
             self.out_all = torch.empty((world * n, 32), dtype=torch.uint8, device="cuda") if world > 1 else None
+            # registered result array: c25519_x25519_shared_sharded runs fused (results stored straight into every rank's array)
+            self.registered = bool(world > 1 and not os.environ.get("C25519_BENCH_NO_REGISTER") and comm.register(self.out_all))
             self.set_bytes = n * 96
         else:
             self.nsets = 2                          # 2 x 172 MB of records > 126 MB L2
@@ -606,9 +608,10 @@ def main():
             res["parity"] = job.parity(inp, outs)
             res["speedup_vs_cpu_baseline"] = {"kernel": res["value"] / cpu["value"], "e2e": res["e2e"]["value"] / cpu["value"]}
             res["config"] = {"workload": WORKLOAD[job.op] % n, "ops_per_gpu_per_step": n,
-                             "parallelism": ("batch sharded %d-way by contiguous index ranges, one NCCL exchange of the result records per step "
-                                             "inside c25519_*_sharded%s" % (world, " (2 slices, 7/8 + 1/8: the first slice's inversion + exchange run under the second slice's ladder)"
-                                                                            if job.op == "x25519_shared" else "")) if world > 1 else "single GPU",
+                             "parallelism": ("batch sharded %d-way by contiguous index ranges inside c25519_*_sharded; %s" % (
+                                 world, "result array registered (CUDA IPC): the batched-inversion kernel stores each result into every rank's "
+                                        "gathered array over NVLink (fused compute + gather, stream-memory-op flags, no collective kernel)"
+                                 if getattr(job, "registered", False) else "one in-place NCCL all-gather of the result records per step")) if world > 1 else "single GPU",
                              "l2": "inputs rotate over %d distinct sets of %d MB > 126 MB L2" % (job.nsets, job.set_bytes >> 20)}
         line = {"metric": top["metric"], "value": top["value"], "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",

@@ -51,6 +51,8 @@ def lib():
         "c25519_ed25519_sign_sharded": ([vp, vp, vp, vp, sz, sz, vp, vp], i32),
         "c25519_ed25519_verify_sharded": ([vp, vp, vp, vp, vp, sz, sz, vp, vp], i32),
         "c25519_allgather_records": ([vp, sz, sz, vp, vp], i32),
+        "c25519_sharded_register": ([vp, sz, vp], i32),
+        "c25519_sharded_unregister": ([vp], i32),
         "c25519_nccl_unique_id": ([vp], i32),
         "c25519_nccl_comm_init": ([C.POINTER(vp), i32, i32, vp, i32], i32),
         "c25519_nccl_comm_destroy": ([vp], i32),

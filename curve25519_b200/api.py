@@ -293,6 +293,15 @@ class ShardedComm:
         idbuf = (C.c_uint8 * 128).from_buffer_copy(uid)
         check(L.c25519_nccl_comm_init(C.byref(self.handle), world, rank, idbuf, int(device)), "c25519_nccl_comm_init")
 
+    def register(self, tensor):
+        """c25519_sharded_register: results written into `tensor` are exchanged by copy-engine pushes into the peers'
+        copies (CUDA IPC) instead of NCCL kernels.  Collective.  Returns False when the memory cannot be shared."""
+        rc = lib().c25519_sharded_register(_p(tensor), tensor.numel() * tensor.element_size(), self.handle)
+        return rc == 0
+
+    def unregister(self, tensor):
+        lib().c25519_sharded_unregister(_p(tensor))
+
     def close(self):
         if self.handle:
             lib().c25519_nccl_comm_destroy(self.handle)

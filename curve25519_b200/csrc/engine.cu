@@ -50,9 +50,10 @@ struct Device {
     const uint32_t* comb = nullptr;                 // device image of the comb table (padded stride)
     cudaStream_t side = nullptr;                    // finish stream: batched inversion + NCCL exchange of a slice
     cudaStream_t aux = nullptr;                     // second compute stream: odd slices' ladders (no drain bubble between slices)
-    std::mutex mu;                                  // guards `pipes`
+    std::mutex mu;                                  // guards `pipes` and `regs`
     std::condition_variable cv;
     std::vector<Pipeline*> pipes;
+    std::vector<struct Registration*> regs;         // result arrays registered for the peer-memory exchange
 };
 Device g_dev[kMaxDevices];
 std::mutex g_init_mu;                               // serialises device initialisation and shutdown
@@ -108,7 +109,12 @@ int ensure_device(int dev)
     CK(cudaMalloc(&t, padded.size() * 4));
     CK(cudaMemcpy(t, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
     d.comb = t;
-    CK(cudaStreamCreateWithFlags(&d.side, cudaStreamNonBlocking));
+    {   // the finish stream outranks the compute streams: when ladder CTAs retire, the waiting inversion / NCCL CTAs of the
+        // previous slice get the freed slots first -- otherwise they would only start once the next ladder's queue is empty
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&d.side, cudaStreamNonBlocking, greatest));
+    }
     CK(cudaStreamCreateWithFlags(&d.aux, cudaStreamNonBlocking));
     {   // keep the stream-ordered scratch allocations of the launchers cached in the pool between calls
         cudaMemPool_t pool;
@@ -333,9 +339,100 @@ int comm_shape(void* comm, int* world, int* rank)
     return 0;
 }
 
-// exchange `cnt` records of `rec` bytes starting at row `row0` of every rank's block of `all` ([world][n_local] records)
-int exchange_rows(uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t cnt, int world, int rank, void* comm, cudaStream_t s)
+// ---- peer-memory exchange: result arrays registered with c25519_sharded_register -----------------------------------------
+// A registered result array is mapped into every rank of the communicator (CUDA IPC).  The exchange of the result records
+// then needs NO SM at all: each rank PUSHES its rows into every peer's array with copy-engine transfers over NVLink
+// (cudaMemcpyAsync on peer-mapped memory) and the ranks synchronise with stream memory operations on peer-mapped flags
+// (cuStreamWriteValue32 / cuStreamWaitValue32).  Unlike NCCL's kernels -- which cannot get SM slots while a ladder grid
+// fills the machine and therefore never overlap it -- the pushes of one slice run underneath the next slice's ladder.
+struct Registration {
+    uint8_t* base = nullptr; size_t bytes = 0; void* comm = nullptr; int world = 0, rank = 0;
+    uint8_t* peer[8] = {};                          // every rank's array in THIS process's address space (peer[rank] = base)
+    uint32_t* flags = nullptr;                      // local flags: entered[8], pushed[8]
+    uint32_t* peer_flags[8] = {};
+    void* opened[16] = {}; int n_opened = 0;        // cudaIpcOpenMemHandle results to close
+    uint32_t epoch = 0;                             // one per exchange call; ranks advance in lock step (collective calls)
+};
+typedef int (*StreamMemOp)(cudaStream_t, unsigned long long, unsigned, unsigned);
+StreamMemOp g_write32 = nullptr, g_wait32 = nullptr;
+typedef int (*MemGetAddressRange)(unsigned long long*, size_t*, unsigned long long);
+MemGetAddressRange g_addr_range = nullptr;
+std::once_flag g_drv_once;
+int driver_load()
 {
+    std::call_once(g_drv_once, [] {
+        cudaDriverEntryPointQueryResult q;
+        void* f = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) g_write32 = (StreamMemOp)f;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) g_wait32 = (StreamMemOp)f;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) g_addr_range = (MemGetAddressRange)f;
+    });
+    if (!g_write32 || !g_wait32 || !g_addr_range) return fail(C25519_E_NO_DEVICE, "CUDA driver lacks stream memory operations");
+    return 0;
+}
+#define DK(expr)                                                        \
+    do {                                                                \
+        int r__ = (expr);                                               \
+        if (r__ != 0) { snprintf(t_err, sizeof t_err, "%s: CUDA driver error %d", #expr, r__); return C25519_E_BAD_ARGUMENT; } \
+    } while (0)
+
+Registration* find_registration(Device& D, const void* p, void* comm)
+{
+    std::lock_guard<std::mutex> lk(D.mu);
+    for (Registration* r : D.regs)
+        if (r->comm == comm && (const uint8_t*)p >= r->base && (const uint8_t*)p < r->base + r->bytes) return r;
+    return nullptr;
+}
+
+// "every rank has entered exchange `epoch`" towards the peers (side stream, no SMs)
+int peer_announce(Registration* R, uint32_t epoch, int slot, cudaStream_t s)
+{
+    for (int p = 0; p < R->world; p++)
+        if (p != R->rank) DK(g_write32(s, (unsigned long long)(uintptr_t)(R->peer_flags[p] + slot * 8 + R->rank), epoch, 0));
+    return 0;
+}
+int peer_await(Registration* R, uint32_t epoch, int slot, cudaStream_t s)
+{
+    for (int p = 0; p < R->world; p++)
+        if (p != R->rank) DK(g_wait32(s, (unsigned long long)(uintptr_t)(R->flags + slot * 8 + p), epoch, 0 /* GEQ */));
+    return 0;
+}
+// push rows [row0, row0 + cnt) of this rank's block into every peer's array (copy engines over NVLink)
+int peer_push(Registration* R, uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t cnt, cudaStream_t s)
+{
+    const size_t off = (size_t)(all - R->base) + ((size_t)R->rank * n_local + row0) * rec;
+    for (int k = 1; k < R->world; k++) {
+        const int p = (R->rank + k) % R->world;      // every rank starts with a different peer
+        CK(cudaMemcpyAsync(R->peer[p] + off, R->base + off, cnt * rec, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+// Exchange `cnt` records of `rec` bytes starting at row `row0` of every rank's block of `all` ([world][n_local] records), on
+// stream `s`.  Registered arrays: copy-engine pushes bracketed by the flag protocol (`first` / `last` mark the first and
+// last slice of one call; epoch from exchange_begin).  Otherwise NCCL: the in-place all-gather for whole blocks, grouped
+// send / recv for a slice.
+struct Exchange { Registration* R = nullptr; uint32_t epoch = 0; };
+int exchange_begin(Exchange& x, Device& D, void* all, void* comm, cudaStream_t s)
+{
+    x.R = find_registration(D, all, comm);
+    if (!x.R) return 0;
+    if (int rc = driver_load()) return rc;
+    x.epoch = ++x.R->epoch;
+    return peer_announce(x.R, x.epoch, 0, s);        // this rank's array may be overwritten from now on (stream order)
+}
+int exchange_rows(Exchange& x, uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t cnt, bool first, bool last, int world, int rank,
+                  void* comm, cudaStream_t s)
+{
+    if (x.R) {
+        if (first) if (int rc = peer_await(x.R, x.epoch, 0, s)) return rc;      // every peer has reached this call
+        if (int rc = peer_push(x.R, all, rec, n_local, row0, cnt, s)) return rc;
+        if (last) {
+            if (int rc = peer_announce(x.R, x.epoch, 1, s)) return rc;          // my rows have landed everywhere
+            return peer_await(x.R, x.epoch, 1, s);                              // everybody's rows have landed here
+        }
+        return 0;
+    }
     if (row0 == 0 && cnt == n_local) {               // whole blocks: the plain in-place all-gather
         NK(g_nccl.AllGather(all + (size_t)rank * n_local * rec, all, n_local * rec, kNcclUint8, comm, s));
         return 0;
@@ -349,16 +446,24 @@ int exchange_rows(uint8_t* all, size_t rec, size_t n_local, size_t row0, size_t 
     NK(g_nccl.GroupEnd());
     return 0;
 }
+// whole-block exchange on the caller's stream (sign / verify / public keys / generic records)
+int exchange_all(Device& D, uint8_t* all, size_t rec, size_t n_local, int world, int rank, void* comm, cudaStream_t s)
+{
+    Exchange x;
+    if (int rc = exchange_begin(x, D, all, comm, s)) return rc;
+    return exchange_rows(x, all, rec, n_local, 0, n_local, true, true, world, rank, comm, s);
+}
 
 // X25519 over a large HBM-resident batch, software-pipelined: the batch is cut into `slices`.  Even slices' ladders run on the
 // caller's stream, odd slices' on the device's aux stream (forked from the caller's stream), so the CTAs of slice i+1 start
 // the moment slots free up while slice i drains -- no bubble at the slice boundary.  Slice i's batched inversion
 // (latency-bound: one 265-operation chain per thread) and -- for the sharded entry point -- its NCCL exchange run on the
 // finish stream underneath the later slices' ladders; only the last slice's finish is exposed.  Everything joins the
-// caller's stream again before the call returns.  `after_slice(row0, cnt, finish_stream)` runs once per slice.
-template <typename AfterSlice>
+// caller's stream again before the call returns.  `before(finish_stream)` runs once after the fork, `after_slice(row0, cnt,
+// first, last, finish_stream)` once per slice.
+template <typename Before, typename AfterSlice>
 int x25519_pipelined(Device& D, uint8_t* out32, const uint8_t* pk32, uint8_t* sk32_inout, size_t n, cudaStream_t s,
-                     const size_t* bounds, int slices, AfterSlice after_slice)
+                     const size_t* bounds, int slices, Before before, AfterSlice after_slice)
 {
     cudaEvent_t ev[8] = {}, fork = nullptr, done = nullptr, aux_done = nullptr;   // per-call events: callers never share one
     int rc = 0, made = 0;
@@ -366,6 +471,8 @@ int x25519_pipelined(Device& D, uint8_t* out32, const uint8_t* pk32, uint8_t* sk
         CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         CK(cudaEventRecord(fork, s));                                 // earlier work on the caller's stream (e.g. the inputs)
         CK(cudaStreamWaitEvent(D.aux, fork, 0));
+        CK(cudaStreamWaitEvent(D.side, fork, 0));
+        if (int r = before(D.side)) return r;
         for (int i = 0; i < slices; i++) {
             const size_t row0 = bounds[i], cnt = bounds[i + 1] - bounds[i];       // bounds[0] = 0 < ... < bounds[slices] = n
             if (cnt == 0) continue;
@@ -376,7 +483,7 @@ int x25519_pipelined(Device& D, uint8_t* out32, const uint8_t* pk32, uint8_t* sk
             CK(cudaEventRecord(ev[i], cs));
             CK(cudaStreamWaitEvent(D.side, ev[i], 0));
             CK(launch_x25519_finish(scratch, out32 + 32 * row0, cnt, D.side));
-            if (int r = after_slice(row0, cnt, D.side)) return r;
+            if (int r = after_slice(row0, cnt, i == 0, i == slices - 1, D.side)) return r;
         }
         CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         CK(cudaEventRecord(done, D.side));
@@ -456,6 +563,12 @@ int c25519_shutdown(void)
                 delete p;
             }
             d.pipes.clear();
+            for (Registration* r : d.regs) {
+                for (int i = 0; i < r->n_opened; i++) cudaIpcCloseMemHandle(r->opened[i]);
+                cudaFree(r->flags);
+                delete r;
+            }
+            d.regs.clear();
         }
         if (d.side) { cudaStreamDestroy(d.side); d.side = nullptr; }
         if (d.aux) { cudaStreamDestroy(d.aux); d.aux = nullptr; }
@@ -631,6 +744,92 @@ int c25519_nccl_comm_destroy(void* comm)
     return 0;
 }
 
+// Map `base[0..bytes)` (device memory of this rank; same size on every rank) into every rank of the communicator.  COLLECTIVE
+// and synchronous.  Afterwards every *_sharded / allgather call whose result array lies inside the region exchanges its
+// records with copy-engine pushes into the peers' arrays + stream-memory-op flags instead of NCCL kernels (see above).
+int c25519_sharded_register(void* base_, size_t bytes, void* nccl_comm)
+{
+    int world = 0, rank = 0;
+    if (int rc = comm_shape(nccl_comm, &world, &rank)) return rc;
+    if (!base_ || bytes == 0) return fail(C25519_E_BAD_ARGUMENT, "null region");
+    if (world > 8) return fail(C25519_E_BAD_ARGUMENT, "peer-memory exchange supports up to 8 ranks (one NVSwitch domain)");
+    if (int rc = driver_load()) return rc;
+    BATCH_PROLOGUE(base_);
+    struct Rec { cudaIpcMemHandle_t data, flags; unsigned long long offset; int ok; };
+    Registration* R = new Registration();
+    R->base = static_cast<uint8_t*>(base_); R->bytes = bytes; R->comm = nccl_comm; R->world = world; R->rank = rank;
+    Rec mine; memset(&mine, 0, sizeof mine);
+    unsigned long long abase = 0; size_t asize = 0;
+    int ok = g_addr_range(&abase, &asize, (unsigned long long)(uintptr_t)base_) == 0;
+    ok = ok && cudaMalloc(&R->flags, 16 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(R->flags, 0, 16 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.data, reinterpret_cast<void*>((uintptr_t)abase)) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.flags, R->flags) == cudaSuccess;
+    cudaGetLastError();
+    mine.offset = (unsigned long long)(uintptr_t)base_ - abase; mine.ok = ok;
+    // all-gather the handles through the communicator itself
+    Rec* d_all = nullptr; Rec h_all[8];
+    CK(cudaMalloc(&d_all, sizeof(Rec) * world));
+    CK(cudaMemcpy(d_all + rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NK(g_nccl.AllGather(d_all + rank, d_all, sizeof(Rec), kNcclUint8, nccl_comm, (cudaStream_t)0));
+    CK(cudaStreamSynchronize((cudaStream_t)0));
+    CK(cudaMemcpy(h_all, d_all, sizeof(Rec) * world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    for (int p = 0; p < world; p++) ok = ok && h_all[p].ok;
+    for (int p = 0; ok && p < world; p++) {
+        if (p == rank) { R->peer[p] = R->base; R->peer_flags[p] = R->flags; continue; }
+        void *pd = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pd, h_all[p].data, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        R->opened[R->n_opened++] = pd;
+        if (cudaIpcOpenMemHandle(&pf, h_all[p].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        R->opened[R->n_opened++] = pf;
+        R->peer[p] = static_cast<uint8_t*>(pd) + h_all[p].offset;
+        R->peer_flags[p] = static_cast<uint32_t*>(pf);
+    }
+    cudaGetLastError();
+    // the decision must be the same on every rank: agree through one more tiny all-gather
+    int* d_ok = nullptr; int h_ok[8];
+    CK(cudaMalloc(&d_ok, sizeof(int) * world));
+    CK(cudaMemcpy(d_ok + rank, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NK(g_nccl.AllGather(d_ok + rank, d_ok, sizeof(int), kNcclUint8, nccl_comm, (cudaStream_t)0));
+    CK(cudaStreamSynchronize((cudaStream_t)0));
+    CK(cudaMemcpy(h_ok, d_ok, sizeof(int) * world, cudaMemcpyDeviceToHost));
+    cudaFree(d_ok);
+    for (int p = 0; p < world; p++) ok = ok && h_ok[p];
+    if (!ok) {
+        for (int i = 0; i < R->n_opened; i++) cudaIpcCloseMemHandle(R->opened[i]);
+        if (R->flags) cudaFree(R->flags);
+        delete R;
+        cudaGetLastError();
+        return fail(C25519_E_BAD_ARGUMENT, "the region cannot be shared through CUDA IPC on every rank (allocate it with cudaMalloc / the default "
+                                           "PyTorch allocator); calls keep using the NCCL exchange");
+    }
+    std::lock_guard<std::mutex> lk(D.mu);
+    D.regs.push_back(R);
+    return 0;
+}
+
+int c25519_sharded_unregister(void* base)
+{
+    for (int dev = 0; dev < kMaxDevices; dev++) {
+        Device& D = g_dev[dev];
+        if (!D.ready.load()) continue;
+        Registration* R = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(D.mu);
+            for (size_t i = 0; i < D.regs.size(); i++)
+                if (D.regs[i]->base == base) { R = D.regs[i]; D.regs.erase(D.regs.begin() + i); break; }
+        }
+        if (!R) continue;
+        DeviceGuard g(dev);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < R->n_opened; i++) cudaIpcCloseMemHandle(R->opened[i]);
+        cudaFree(R->flags);
+        delete R;
+        return 0;
+    }
+    return fail(C25519_E_BAD_ARGUMENT, "region was not registered");
+}
+
 int c25519_allgather_records(void* all, size_t rec_bytes, size_t n_local, void* nccl_comm, void* stream)
 {
     int world = 0, rank = 0;
@@ -638,12 +837,11 @@ int c25519_allgather_records(void* all, size_t rec_bytes, size_t n_local, void* 
     if (n_local == 0 || rec_bytes == 0) return 0;
     if (!all) return fail(C25519_E_BAD_ARGUMENT, "null pointer");
     BATCH_PROLOGUE(all);
-    return exchange_rows(static_cast<uint8_t*>(all), rec_bytes, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream);
+    return world > 1 ? exchange_all(D, static_cast<uint8_t*>(all), rec_bytes, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
 }
 
 // X25519 shared keys, sharded: this rank computes rows [rank*n_local, (rank+1)*n_local) of out_all and receives the other
-// ranks' rows.  The local batch is cut into two slices; the first slice's batched inversion and NCCL exchange run on a side
-// stream underneath the second slice's ladder, so only the last slice's finish + transfer is exposed.
+// ranks' rows.
 int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, uint8_t* sk32_local_inout, size_t n_local,
                                  void* nccl_comm, void* stream)
 {
@@ -655,18 +853,40 @@ int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, ui
     BATCH_PROLOGUE(out_all, pk32_local, sk32_local_inout);
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t* mine = out_all + (size_t)rank * n_local * 32;
-    if (n_local < kPipelineMinOps) {
+    // Registered result array: the fused path.  The batched-inversion kernel stores every result straight into ALL ranks'
+    // arrays through the peer mappings (k_normalize_scatter: 32-byte stores over NVLink), bracketed by the stream-memory-op
+    // flag protocol; no separate collective runs at all.  Measured best at every N.
+    if (world > 1) {
+        if (Registration* R = find_registration(D, out_all, nccl_comm)) {
+            if (int rc = driver_load()) return rc;
+            const uint32_t epoch = ++R->epoch;
+            uint8_t* ptrs[8] = {};
+            for (int g = 0; g < world; g++) ptrs[g] = R->peer[g] + (out_all - R->base);
+            if (int rc = peer_announce(R, epoch, 0, s)) return rc;          // my array may be overwritten from here on
+            if (int rc = peer_await(R, epoch, 0, s)) return rc;             // ... and so may everybody else's
+            CK(launch_x25519_ladder_scatter(ptrs, world, rank, pk32_local, sk32_local_inout, n_local, s));
+            if (int rc = peer_announce(R, epoch, 1, s)) return rc;          // my rows have landed everywhere
+            return peer_await(R, epoch, 1, s);                              // everybody's rows have landed here
+        }
+    }
+    // Unregistered: local kernels, then the in-place NCCL all-gather.  C25519_SHARD_MODE=1 selects the two-slice pipeline
+    // (first slice's inversion + exchange on a side stream under the second slice's ladder); it was measured SLOWER at
+    // N = 2 and N = 8 (the finish kernels get no SM slots while a ladder grid fills the machine), so it is not the default.
+    static const int shard_mode = [] { const char* e = getenv("C25519_SHARD_MODE"); return e ? atoi(e) : 0; }();
+    if (n_local < kPipelineMinOps || shard_mode == 0) {
         CK(launch_x25519_ladder(mine, pk32_local, sk32_local_inout, n_local, s));
-        if (world > 1) return exchange_rows(out_all, 32, n_local, 0, n_local, world, rank, nccl_comm, s);
+        if (world > 1) return exchange_all(D, out_all, 32, n_local, world, rank, nccl_comm, s);
         return 0;
     }
-    // Two slices, 7/8 + 1/8: the big slice's inversion and exchange (the bulk of the transfer) hide under the small slice's
-    // ladder; only the small slice's finish + an eighth of the transfer are exposed, and there is a single slice boundary.
-    const size_t cut = (n_local - n_local / 8 + 127) & ~(size_t)127;
+    static const int shard_den = [] { const char* e = getenv("C25519_SHARD_TAIL_DEN"); return e ? atoi(e) : 8; }();  // last slice = 1/den
+    const size_t cut = (n_local - n_local / (size_t)shard_den + 127) & ~(size_t)127;
     const size_t bounds[3] = {0, cut, n_local};
-    return x25519_pipelined(D, mine, pk32_local, sk32_local_inout, n_local, s, bounds, 2, [&](size_t row0, size_t cnt, cudaStream_t side) -> int {
-        return world > 1 ? exchange_rows(out_all, 32, n_local, row0, cnt, world, rank, nccl_comm, side) : 0;
-    });
+    Exchange x;
+    return x25519_pipelined(D, mine, pk32_local, sk32_local_inout, n_local, s, bounds, 2,
+        [&](cudaStream_t side) -> int { return world > 1 ? exchange_begin(x, D, out_all, nccl_comm, side) : 0; },
+        [&](size_t row0, size_t cnt, bool first, bool last, cudaStream_t side) -> int {
+            return world > 1 ? exchange_rows(x, out_all, 32, n_local, row0, cnt, first, last, world, rank, nccl_comm, side) : 0;
+        });
 }
 
 int c25519_x25519_public_sharded(uint8_t* pk_all, uint8_t* sk32_local_inout, size_t n_local, int ladder, void* nccl_comm, void* stream)
@@ -680,7 +900,7 @@ int c25519_x25519_public_sharded(uint8_t* pk_all, uint8_t* sk32_local_inout, siz
     uint8_t* mine = pk_all + (size_t)rank * n_local * 32;
     if (ladder) CK(launch_x25519_ladder(mine, nullptr, sk32_local_inout, n_local, (cudaStream_t)stream));
     else CK(launch_x25519_comb(mine, sk32_local_inout, n_local, D.comb, (cudaStream_t)stream));
-    return world > 1 ? exchange_rows(pk_all, 32, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
+    return world > 1 ? exchange_all(D, pk_all, 32, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
 }
 
 int c25519_ed25519_sign_sharded(uint8_t* sig_all, const uint8_t* priv64_local, const uint8_t* msgs_local, const uint64_t* msg_off_local,
@@ -693,7 +913,7 @@ int c25519_ed25519_sign_sharded(uint8_t* sig_all, const uint8_t* priv64_local, c
     if (misaligned32(sig_all) || misaligned32(priv64_local)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     BATCH_PROLOGUE(sig_all, priv64_local);
     CK(launch_ed25519_sign(sig_all + (size_t)rank * n_local * 64, priv64_local, msgs_local, msg_off_local, fixed_len, n_local, D.comb, (cudaStream_t)stream));
-    return world > 1 ? exchange_rows(sig_all, 64, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
+    return world > 1 ? exchange_all(D, sig_all, 64, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
 }
 
 int c25519_ed25519_verify_sharded(int32_t* ok_all, const uint8_t* sig64_local, const uint8_t* pk32_local, const uint8_t* msgs_local,
@@ -706,7 +926,7 @@ int c25519_ed25519_verify_sharded(int32_t* ok_all, const uint8_t* sig64_local, c
     if (misaligned32(sig64_local) || misaligned32(pk32_local)) return fail(C25519_E_BAD_ARGUMENT, "record arrays must be 32-byte aligned");
     BATCH_PROLOGUE(ok_all, sig64_local, pk32_local);
     CK(launch_ed25519_verify(ok_all + (size_t)rank * n_local, sig64_local, pk32_local, msgs_local, msg_off_local, fixed_len, n_local, D.comb, (cudaStream_t)stream));
-    return world > 1 ? exchange_rows(reinterpret_cast<uint8_t*>(ok_all), 4, n_local, 0, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
+    return world > 1 ? exchange_all(D, reinterpret_cast<uint8_t*>(ok_all), 4, n_local, world, rank, nccl_comm, (cudaStream_t)stream) : 0;
 }
 
 // ------------------------------------------------------------------ host-pointer batch API

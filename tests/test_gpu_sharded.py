@@ -71,6 +71,22 @@ def _worker(rank, world, port, n_local, q):
         exp, exp_sk = o.x25519_shared(pk, sk, threads=T)
         assert (out_all.cpu().numpy() == exp).all(), "gathered shared keys differ on rank %d" % rank
         assert (d_sk.cpu().numpy() == exp_sk[lo:hi]).all()
+        # the same call on a REGISTERED result array: fused path (the inversion kernel stores into every rank's array through
+        # CUDA IPC mappings, stream-memory-op flags, no NCCL kernel); twice, to exercise the epoch protocol
+        reg_all = torch.zeros((n, 32), dtype=torch.uint8, device="cuda")
+        assert comm.register(reg_all), "c25519_sharded_register failed"
+        for rep in range(2):
+            reg_all.zero_(); torch.cuda.synchronize(); dist.barrier()
+            api.x25519_shared_sharded(comm, reg_all, torch.from_numpy(pk[lo:hi]).cuda(), torch.from_numpy(sk[lo:hi]).cuda())
+            torch.cuda.synchronize()
+            assert (reg_all.cpu().numpy() == exp).all(), "fused gathered shared keys differ on rank %d (rep %d)" % (rank, rep)
+        # generic records on the registered array: copy-engine pushes
+        reg_all.zero_(); reg_all[lo:hi] = torch.from_numpy(exp[lo:hi]).cuda(); torch.cuda.synchronize(); dist.barrier()
+        api.allgather_records(comm, reg_all, n_local)
+        torch.cuda.synchronize()
+        assert (reg_all.cpu().numpy() == exp).all(), "pushed records differ on rank %d" % rank
+        dist.barrier()
+        comm.unregister(reg_all)
         # --- Ed25519 sign + verify, sharded
         e_pub, e_priv = o.ed25519_keypair(seed, threads=T)
         elo, ehi = rank * ne_local, (rank + 1) * ne_local
