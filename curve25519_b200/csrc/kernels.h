@@ -36,6 +36,9 @@ cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size
                              uint8_t* out2, size_t out2_stride, const uint8_t* cmp, size_t cmp_stride, int32_t* ok, cudaStream_t s);
 // below this many operations a batch is latency-bound and each kernel does its own inversion (one launch)
 constexpr size_t kDeferThreshold = 256;
+// below this many operations the X25519 ladder runs warp-cooperatively, four lanes per operation (x25519.cuh:
+// mont_step_quad): ~370 us per batch instead of ~620 us, at a quarter of the throughput -- which a batch this small cannot use
+constexpr size_t kQuadThreshold = 8192;
 
 cudaError_t launch_modl(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n, cudaStream_t s);
 cudaError_t launch_legacy_op(int op, uint32_t* io, int nin, const uint32_t* table, cudaStream_t s);

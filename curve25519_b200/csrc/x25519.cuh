@@ -143,6 +143,84 @@ C25519_DEV void x25519_ladder_projective_raw(fe& PX, fe& PZ, const fe& u, KeyWor
     fe_select(PZ, R1Z, R0Z, cur);
 }
 
+// ---- warp-cooperative ladder for SMALL batches: one scalar multiplication per 4-lane group --------------------------------
+// With fewer operations than the machine has thread slots, throughput is irrelevant and the latency of one dependent chain
+// (254 steps x 10 field operations back to back) is all that counts.  A ladder step has only three multiplication LEVELS:
+//     level 1:  DA = A.D      CB = B.C      PP = P^2       MM = M^2            (P, M = x+z, x-z of the point being doubled)
+//     level 2:  (DA+CB)^2     (DA-CB)^2     PP.MM          121665.(PP-MM)
+//     level 3:               u.(DA-CB)^2                   (PP-MM).(PP + 121665 (PP-MM))
+// so four lanes, each executing ONE field multiplication per level on its own operands and trading results through
+// __shfl_sync, walk a step in three multiplication latencies instead of ten.  Every lane keeps a full copy of the state
+// (SX, SZ, DX, DZ); the additions are replicated (cheap).  Same rational maps as mont_step_sel, hence the same results.
+C25519_DEV void fe_shfl_xor(fe& out, const fe& in, int mask)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.v[i] = __shfl_xor_sync(0xffffffffu, in.v[i], mask);
+}
+C25519_DEV void fe_bcast4(fe& out, const fe& in, int role)         // value held by lane `role` of each 4-lane group
+{
+    const int src = (threadIdx.x & 28) | role;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.v[i] = __shfl_sync(0xffffffffu, in.v[i], src);
+}
+C25519_DEV void fe_pick4(fe& out, int role, const fe& r0, const fe& r1, const fe& r2, const fe& r3)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 a = (role & 1) ? r1.v[i] : r0.v[i], b = (role & 1) ? r3.v[i] : r2.v[i];
+        out.v[i] = (role & 2) ? b : a;
+    }
+}
+// one step; on entry and exit all four lanes hold identical narrow (SX, SZ, DX, DZ)
+C25519_DEV void mont_step_quad(fe& SX, fe& SZ, fe& DX, fe& DZ, bool dbl_s, const fe& u, int role)
+{
+    fe A, B, C, D, P, M, op1, op2, r, other;
+    fe_sub(A, SX, SZ); fe_add_nn(B, SX, SZ); fe_sub(C, DX, DZ); fe_add_nn(D, DX, DZ);
+    fe_select(P, D, B, dbl_s); fe_select(M, C, A, dbl_s);
+    // level 1: lane 0: A.D   lane 1: B.C   lane 2: P.P   lane 3: M.M
+    fe_pick4(op1, role, A, B, P, M); fe_pick4(op2, role, D, C, P, M);
+    fe_mul(r, op1, op2);
+    fe_shfl_xor(other, r, 1);                      // lanes 0 <-> 1 trade DA / CB, lanes 2 <-> 3 trade PP / MM
+    // level 2 operands: lane 0: (DA+CB)^2   lane 1: (DA-CB)^2   lane 2: PP.MM   lane 3: (PP-MM) . 121665
+    fe sum, dif, k;
+    fe_add_nn(sum, r, other);
+    if (role & 1) fe_sub(dif, other, r); else fe_sub(dif, r, other);     // lane 1: DA - CB, lane 3: PP - MM (lanes 0, 2: unused sign)
+    fe_set_u32(k, 121665u);
+    fe_pick4(op1, role, sum, dif, r, dif); fe_pick4(op2, role, sum, dif, other, k);
+    fe r2;
+    fe_mul(r2, op1, op2);
+    // level 3: lane 1: u . (DA-CB)^2    lane 3: E . (PP + 121665 E), E = PP - MM (lane 3 holds MM in r, PP in other)
+    fe F; fe_add_nn(F, other, r2);                 // meaningful on lane 3 only: PP + 121665 E
+    fe_pick4(op1, role, r2, r2, r2, dif); fe_pick4(op2, role, r2, u, r2, F);
+    fe r3;
+    fe_mul(r3, op1, op2);
+    // results: SX' = lane 0's r2, SZ' = lane 1's r3, DX' = lane 2's r2, DZ' = lane 3's r3
+    fe_bcast4(SX, r2, 0); fe_bcast4(SZ, r3, 1); fe_bcast4(DX, r2, 2); fe_bcast4(DZ, r3, 3);
+}
+
+// canonical x-coordinate of [k]u by the four-lane ladder (k clamped: bit 254 set, bit 255 clear); all four lanes return it
+template <typename KeyWord>
+C25519_DEV void x25519_ladder_quad(fe& out, const fe& u, KeyWord kw, int role)
+{
+    fe R0X, R0Z, R1X, R1Z;
+    fe_copy(R0X, u); fe_set_u32(R0Z, 1);
+    mont_double(R1X, R1Z, R0X, R0Z);
+    fe_narrow(R0X);
+    bool cur = true;
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; --bit) {
+        bool b = (kw(bit >> 5) >> (bit & 31)) & 1u;
+        bool s = (b != cur);
+        cur = b;
+        mont_step_quad(R0X, R0Z, R1X, R1Z, s, u, role);
+    }
+    fe PX, PZ, zi;
+    fe_select(PX, R1X, R0X, cur); fe_select(PZ, R1Z, R0Z, cur);
+    fe_invert(zi, PZ);
+    fe_mul(out, PX, zi);
+    fe_canon(out);
+}
+
 // out = canonical x-coordinate of [k]u (single-operation form: own inversion).
 template <typename KeyWord>
 C25519_DEV void x25519_ladder(fe& out, const fe& u, KeyWord kw)

@@ -52,6 +52,27 @@ k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, u
     }
 }
 
+// Small batches (n < kDeferThreshold): one operation per 4-lane group, 32 operations per 128-thread CTA (x25519.cuh:
+// mont_step_quad).  The four lanes of a group load the same records, run the cooperative ladder, lane 0 stores.
+__global__ void __launch_bounds__(kLadderThreads)
+k_x25519_ladder_quad(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n)
+{
+    const int role = threadIdx.x & 3;
+    size_t i = (size_t)blockIdx.x * (kLadderThreads / 4) + (threadIdx.x >> 2);
+    const bool live = i < n;
+    if (!live) i = n - 1;                              // keep whole warps converged for the shuffles; no stores from dead groups
+    fe k;
+    fe_load_plain(k, sk32 + 32 * i);
+    k.v[0] &= 0xfffffff8u;
+    k.v[7] = (k.v[7] | 0x40000000u) & 0x7fffffffu;
+    fe u;
+    if (pk32) fe_load(u, pk32 + 32 * i); else fe_set_u32(u, 9);
+    __syncwarp();                                      // every lane of the group has read sk before lane 0 overwrites it
+    fe r;
+    x25519_ladder_quad(r, u, [&](int w) { return k.v[w]; }, role);
+    if (live && role == 0) { fe_store(sk32 + 32 * i, k); fe_store(out32 + 32 * i, r); }
+}
+
 // Generic scalar multiplication, no clamping, scalar NOT modified (ecp_PointMultiply, curve25519_dh.c:94).
 __global__ void __launch_bounds__(kLadderThreads)
 k_x25519_ladder_raw(const uint8_t* __restrict__ pk32, const uint8_t* __restrict__ k32, size_t n, uint8_t* __restrict__ scratch)
@@ -207,8 +228,8 @@ cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, ui
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
-    if (n < kDeferThreshold) {
-        k_x25519_ladder<false><<<grid, kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n, nullptr);
+    if (n < kQuadThreshold) {                          // latency-bound: four lanes per operation
+        k_x25519_ladder_quad<<<(unsigned)((n + kLadderThreads / 4 - 1) / (kLadderThreads / 4)), kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n);
         count_launch();
         return cudaGetLastError();
     }
