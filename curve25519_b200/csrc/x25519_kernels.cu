@@ -20,6 +20,8 @@ constexpr int kLadderThreads = 128;
 // DEFER = true : stop at the projective result, write (X, Z) to the 96-byte scratch record i; the affine
 //                result is produced for all operations by k_normalize (one shared inversion per 16 operations).
 // DEFER = false: finish in place with a private inversion (tiny, latency-bound batches; the n = 1 legacy calls).
+// ptxas settles on 98 registers (4 resident CTAs = 16 warps per SM).  Forcing 5 CTAs (<= 96 registers) makes it spill 36 bytes
+// inside the loop; launch shapes between 16 and 21 warps per SM all land within 1 % anyway (profiles/r2_ladder_lab2.txt).
 template <bool DEFER>
 __global__ void __launch_bounds__(kLadderThreads)
 k_x25519_ladder(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n,
