@@ -179,6 +179,22 @@ def cpu_run(o, op, inp, threads):
     return o.last_seconds, {"ok": ok}
 
 
+def cpu_baseline_asm64(op, inp, threads):
+    """Optional: the reference's x86-64 assembly build on the same sample (its fastest CPU configuration)."""
+    from oracle import pyoracle
+    if not pyoracle.available("reference_asm"):
+        return None
+    try:
+        o = pyoracle.Oracle("reference_asm")
+        cpu_run(o, op, {k: v[:threads * 8] for k, v in inp.items()}, threads)
+        secs, _ = cpu_run(o, op, inp, threads)
+        n_ops = next(iter(inp.values())).shape[0]
+        return {"value": n_ops / secs, "unit": "ops/s", "cores": threads, "kind": "reference-asm64",
+                "sample": "%d ops, %d pthreads, %.2f s (source/asm64 build of the reference)" % (n_ops, threads, secs)}
+    except Exception as ex:                         # pragma: no cover
+        return {"unavailable": repr(ex)[:200]}
+
+
 def cpu_baseline(op, kind_pref, threads):
     o = _oracle(kind_pref)
     per_core = 6000 if op == "x25519_shared" else 3000          # ~1.1 s / ~0.9 s of CPU work per core
@@ -209,7 +225,9 @@ def reference_measure(op, steps, warmup, threads):
         t += s
     val = per_step * steps / t
     call = "curve25519_dh_CreateSharedKey" if op == "x25519_shared" else "ed25519_VerifySignature"
-    return {"metric": METRICS[op], "value": val, "unit": "ops/s", "ms_per_step": 1e3 * t / steps,
+    asm = cpu_baseline_asm64(op, inp, threads)
+    extra = {"cpu_baseline_asm64": asm} if asm is not None else {}
+    return {**extra, "metric": METRICS[op], "value": val, "unit": "ops/s", "ms_per_step": 1e3 * t / steps,
             "config": {"workload": "%s, reference portable-C on host cores" % (WORKLOAD[op] % per_step).replace(" per GPU", "").replace(", bit-exact vs reference", ""),
                        "ops_per_step": per_step, "host_threads": threads},
             "cpu_baseline": {"value": val, "unit": "ops/s", "cores": threads, "kind": o.kind,
@@ -605,6 +623,9 @@ def main():
         for res, job in ((top, top_job), (sub, sub_job)):
             cpu, inp, outs = cpu_baseline(job.op, args.cpu_kind, threads)
             res["cpu_baseline"] = cpu
+            asm = cpu_baseline_asm64(job.op, inp, threads)
+            if asm is not None:
+                res["cpu_baseline_asm64"] = asm
             res["parity"] = job.parity(inp, outs)
             res["speedup_vs_cpu_baseline"] = {"kernel": res["value"] / cpu["value"], "e2e": res["e2e"]["value"] / cpu["value"]}
             res["config"] = {"workload": WORKLOAD[job.op] % n, "ops_per_gpu_per_step": n,

@@ -3,6 +3,7 @@
     Oracle("port")       -> oracle/liboracle25519.so   (our C restatement, oracle25519.c)
     Oracle("reference")  -> oracle/_ref/libref25519.so (the reference's own portable-C sources,
                                                        compiled unmodified by oracle/Makefile)
+    Oracle("reference_asm") -> oracle/_ref/libref25519_asm.so (the reference's asm64 build, "best CPU" baseline)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
 this module.  Nothing under curve25519_b200/ does.
@@ -22,6 +23,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PATHS = {
     "port": os.path.join(_HERE, "liboracle25519.so"),
     "reference": os.path.join(_HERE, "_ref", "libref25519.so"),
+    # the reference's x86-64 assembly build (source/asm64), its fastest CPU configuration: optional second baseline
+    "reference_asm": os.path.join(_HERE, "_ref", "libref25519_asm.so"),
 }
 
 

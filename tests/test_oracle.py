@@ -211,3 +211,21 @@ def test_golden_fixtures(oracles, name):
             tampered = _rows(g["sig_tampered"])
             ok = o.ed25519_verify(tampered, pub, flat, off)
             assert ok.tolist() == g["ok_tampered"], oname
+
+
+def test_asm64_reference_build_agrees_with_portable_c(rng):
+    """The optional "best CPU" baseline (the reference's source/asm64 build) computes the same bytes as its portable C."""
+    from oracle import pyoracle
+    if not (pyoracle.available("reference_asm") and pyoracle.available("reference")):
+        pytest.skip("reference builds not present on this box")
+    A, R = pyoracle.Oracle("reference_asm"), pyoracle.Oracle("reference")
+    n = 256
+    sk = rng.integers(0, 256, (n, 32), dtype=np.uint8); pk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+    assert (A.x25519_shared(pk, sk, threads=4)[0] == R.x25519_shared(pk, sk, threads=4)[0]).all()
+    pa, va = A.ed25519_keypair(sk, threads=4); pr, vr = R.ed25519_keypair(sk, threads=4)
+    assert (pa == pr).all()
+    sa = A.ed25519_sign(va, msgs, threads=4)
+    assert (sa == R.ed25519_sign(vr, msgs, threads=4)).all()
+    sa[::3, 5] ^= 1
+    assert (A.ed25519_verify(sa, pa, msgs, threads=4) == R.ed25519_verify(sa, pr, msgs, threads=4)).all()
