@@ -53,6 +53,8 @@ def lib():
         "c25519_allgather_records": ([vp, sz, sz, vp, vp], i32),
         "c25519_sharded_register": ([vp, sz, vp], i32),
         "c25519_sharded_unregister": ([vp], i32),
+        "c25519_sharded_set_deferred": ([vp, i32], i32),
+        "c25519_sharded_sync": ([vp, vp], i32),
         "c25519_nccl_unique_id": ([vp], i32),
         "c25519_nccl_comm_init": ([C.POINTER(vp), i32, i32, vp, i32], i32),
         "c25519_nccl_comm_destroy": ([vp], i32),

@@ -302,6 +302,13 @@ class ShardedComm:
     def unregister(self, tensor):
         lib().c25519_sharded_unregister(_p(tensor))
 
+    def set_deferred(self, tensor, on=True):
+        """Deferred exchange on a registered array: the transfer to the peers overlaps the caller's next work; sync() joins it."""
+        check(lib().c25519_sharded_set_deferred(_p(tensor), 1 if on else 0), "c25519_sharded_set_deferred")
+
+    def sync(self, tensor):
+        check(lib().c25519_sharded_sync(_p(tensor), _stream()), "c25519_sharded_sync")
+
     def close(self):
         if self.handle:
             lib().c25519_nccl_comm_destroy(self.handle)

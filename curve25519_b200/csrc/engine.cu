@@ -352,6 +352,11 @@ struct Registration {
     uint32_t* peer_flags[8] = {};
     void* opened[16] = {}; int n_opened = 0;        // cudaIpcOpenMemHandle results to close
     uint32_t epoch = 0;                             // one per exchange call; ranks advance in lock step (collective calls)
+    // deferred mode (c25519_sharded_set_deferred): the exchange runs on `xs` and is NOT joined into the caller's stream;
+    // `done` marks its completion (c25519_sharded_sync, and the next call's write-after-read guard)
+    bool deferred = false, has_done = false;
+    cudaStream_t xs = nullptr;
+    cudaEvent_t done = nullptr;
 };
 typedef int (*StreamMemOp)(cudaStream_t, unsigned long long, unsigned, unsigned);
 StreamMemOp g_write32 = nullptr, g_wait32 = nullptr;
@@ -566,6 +571,8 @@ int c25519_shutdown(void)
             for (Registration* r : d.regs) {
                 for (int i = 0; i < r->n_opened; i++) cudaIpcCloseMemHandle(r->opened[i]);
                 cudaFree(r->flags);
+                if (r->xs) cudaStreamDestroy(r->xs);
+                if (r->done) cudaEventDestroy(r->done);
                 delete r;
             }
             d.regs.clear();
@@ -824,10 +831,51 @@ int c25519_sharded_unregister(void* base)
         cudaDeviceSynchronize();
         for (int i = 0; i < R->n_opened; i++) cudaIpcCloseMemHandle(R->opened[i]);
         cudaFree(R->flags);
+        if (R->xs) cudaStreamDestroy(R->xs);
+        if (R->done) cudaEventDestroy(R->done);
         delete R;
         return 0;
     }
     return fail(C25519_E_BAD_ARGUMENT, "region was not registered");
+}
+
+static Registration* registration_by_base(void* base, int* dev_out)
+{
+    for (int dev = 0; dev < kMaxDevices; dev++) {
+        Device& D = g_dev[dev];
+        if (!D.ready.load()) continue;
+        std::lock_guard<std::mutex> lk(D.mu);
+        for (Registration* r : D.regs) if (r->base == base) { *dev_out = dev; return r; }
+    }
+    return nullptr;
+}
+
+// Deferred exchange for a registered region: c25519_x25519_shared_sharded then returns (stream order) as soon as THIS rank's rows
+// are in place; the rows travel to the peers by copy engine on a private stream, underneath whatever the caller enqueues next
+// (typically the next batch's ladder -- copy engines need no SM).  The gathered array is complete after c25519_sharded_sync.
+int c25519_sharded_set_deferred(void* base, int on)
+{
+    int dev = 0;
+    Registration* R = registration_by_base(base, &dev);
+    if (!R) return fail(C25519_E_BAD_ARGUMENT, "region was not registered");
+    DeviceGuard g(dev);
+    if (on && !R->xs) {
+        CK(cudaStreamCreateWithFlags(&R->xs, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&R->done, cudaEventDisableTiming));
+    }
+    R->deferred = on != 0;
+    return 0;
+}
+
+// make `stream` wait for the last deferred exchange on the region (no-op when none is pending)
+int c25519_sharded_sync(void* base, void* stream)
+{
+    int dev = 0;
+    Registration* R = registration_by_base(base, &dev);
+    if (!R) return fail(C25519_E_BAD_ARGUMENT, "region was not registered");
+    DeviceGuard g(dev);
+    if (R->has_done) CK(cudaStreamWaitEvent((cudaStream_t)stream, R->done, 0));
+    return 0;
 }
 
 int c25519_allgather_records(void* all, size_t rec_bytes, size_t n_local, void* nccl_comm, void* stream)
@@ -859,6 +907,30 @@ int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, ui
     if (world > 1) {
         if (Registration* R = find_registration(D, out_all, nccl_comm)) {
             if (int rc = driver_load()) return rc;
+            if (R->deferred && n_local >= kQuadThreshold) {
+                // Deferred: ladder now; my rows are rewritten only after the previous exchange has finished reading them; the
+                // push to the peers runs on the registration's own stream (copy engines + flag operations, no SM) and is not
+                // joined here -- it overlaps the caller's next work.  c25519_sharded_sync joins it.
+                const uint32_t epoch = ++R->epoch;
+                uint8_t* scratch = nullptr;
+                CK(launch_x25519_projective(&scratch, pk32_local, sk32_local_inout, n_local, s));
+                if (R->has_done) CK(cudaStreamWaitEvent(s, R->done, 0));
+                CK(launch_x25519_finish(scratch, mine, n_local, s));
+                cudaEvent_t ev = nullptr;
+                CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                cudaError_t e = cudaEventRecord(ev, s);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(R->xs, ev, 0);
+                cudaEventDestroy(ev);
+                if (e != cudaSuccess) return fail((int)e, "deferred exchange: event");
+                if (int rc = peer_announce(R, epoch, 0, R->xs)) return rc;
+                if (int rc = peer_await(R, epoch, 0, R->xs)) return rc;
+                if (int rc = peer_push(R, out_all, 32, n_local, 0, n_local, R->xs)) return rc;
+                if (int rc = peer_announce(R, epoch, 1, R->xs)) return rc;
+                if (int rc = peer_await(R, epoch, 1, R->xs)) return rc;
+                CK(cudaEventRecord(R->done, R->xs));
+                R->has_done = true;
+                return 0;
+            }
             const uint32_t epoch = ++R->epoch;
             uint8_t* ptrs[8] = {};
             for (int g = 0; g < world; g++) ptrs[g] = R->peer[g] + (out_all - R->base);

@@ -80,6 +80,16 @@ def _worker(rank, world, port, n_local, q):
             api.x25519_shared_sharded(comm, reg_all, torch.from_numpy(pk[lo:hi]).cuda(), torch.from_numpy(sk[lo:hi]).cuda())
             torch.cuda.synchronize()
             assert (reg_all.cpu().numpy() == exp).all(), "fused gathered shared keys differ on rank %d (rep %d)" % (rank, rep)
+        # deferred exchange: three batches back to back (each transfer under the next ladder), joined once at the end
+        comm.set_deferred(reg_all, True)
+        rng2 = np.random.Generator(np.random.PCG64(0xDEF))
+        batches = [(rng2.integers(0, 256, (n, 32), dtype=np.uint8), rng2.integers(0, 256, (n, 32), dtype=np.uint8)) for _ in range(3)]
+        for bsk, bpk in batches:
+            api.x25519_shared_sharded(comm, reg_all, torch.from_numpy(bpk[lo:hi]).cuda(), torch.from_numpy(bsk[lo:hi]).cuda())
+        comm.sync(reg_all); torch.cuda.synchronize(); dist.barrier()
+        exp3, _ = o.x25519_shared(batches[2][1], batches[2][0], threads=T)
+        assert (reg_all.cpu().numpy() == exp3).all(), "deferred gathered shared keys differ on rank %d" % rank
+        comm.set_deferred(reg_all, False)
         # generic records on the registered array: copy-engine pushes
         reg_all.zero_(); reg_all[lo:hi] = torch.from_numpy(exp[lo:hi]).cuda(); torch.cuda.synchronize(); dist.barrier()
         api.allgather_records(comm, reg_all, n_local)

@@ -42,6 +42,22 @@ reg = comm.register(out_all)
 k[0] = 0; sharded(); torch.cuda.synchronize(); dist.barrier()
 same = bool(torch.equal(out_all, ref))
 d, e = timeit(sharded), timeit(plain_then_gather)
+comm.set_deferred(out_all, True)
+def timeit_deferred(steps=10):
+    for _ in range(3): sharded()
+    comm.sync(out_all); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): sharded()
+    comm.sync(out_all)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+f = timeit_deferred()
+k[0] = 0; out_all.zero_(); torch.cuda.synchronize(); dist.barrier(); sharded(); comm.sync(out_all); torch.cuda.synchronize(); dist.barrier()
+same_def = bool(torch.equal(out_all, ref))
+if rank == 0:
+    print("world %d deferred exchange (copy engines under the next step's ladder; last one joined): %.3f ms per step, matches NCCL: %s" % (world, f, same_def), flush=True)
 if rank == 0:
     print("world %d mode %s den %s: plain %.3f ms | NCCL: sharded entry %.3f, batch + allgather %.3f | registered=%s (matches NCCL: %s): sharded entry %.3f, batch + allgather %.3f" %
           (world, os.environ.get("C25519_SHARD_MODE", "1"), os.environ.get("C25519_SHARD_TAIL_DEN", "8"), a, b, c, reg, same, d, e), flush=True)
