@@ -259,3 +259,58 @@ def test_long_messages(engine, oracle, rng):
     ok = engine.ed25519_verify(_dev(bad), _dev(pub), _dev(flat), d_off).cpu().numpy()
     assert ok.tolist() == [1, 0, 1, 1, 1, 1, 1, 1]
     assert (engine.ed25519_sign(priv, flat, off) == exp).all()
+
+
+def test_ragged_host_path_is_sliced(engine, oracle, rng):
+    """Ragged messages through the HOST-pointer ABI with more operations than one pipeline slice holds (2^17): the slices are
+    staged with unmodified offsets and a message base pointer shifted back by the slice's first offset; results must equal the
+    device-pointer path on the same inputs, and a sample must equal the oracle."""
+    import torch
+    n = (1 << 17) * 2 + 12345
+    lens = rng.integers(0, 41, n)
+    lens[: 16] = [0, 1, 15, 16, 17, 40, 0, 0, 39, 2, 3, 4, 5, 6, 7, 8]
+    off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+    flat = rng.integers(0, 256, int(off[-1]), dtype=np.uint8)
+    seed = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    pub, priv = engine.ed25519_keypair(seed)                       # host path (fixed-size records)
+    sig_h = engine.ed25519_sign(priv, flat, off)                   # host path, ragged: three slices
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    sig_d = engine.ed25519_sign(_dev(priv), _dev(flat), d_off).cpu().numpy()
+    assert (sig_h == sig_d).all()
+    bad = sig_h.copy(); bad[::7, 33] ^= 2
+    ok_h = engine.ed25519_verify(bad, pub, flat, off)
+    ok_d = engine.ed25519_verify(_dev(bad), _dev(pub), _dev(flat), d_off).cpu().numpy()
+    assert (ok_h == ok_d).all() and (ok_h[::7] == 0).all() and ok_h.sum() == n - len(range(0, n, 7))
+    idx = np.concatenate([np.arange(64), np.arange((1 << 17) - 32, (1 << 17) + 32), np.arange(n - 64, n)])   # around the slice boundaries
+    s_off = np.zeros(idx.size + 1, np.uint64); s_off[1:] = np.cumsum(lens[idx])
+    s_flat = np.concatenate([flat[int(off[i]):int(off[i + 1])] for i in idx]) if s_off[-1] else np.zeros(0, np.uint8)
+    e_pub, e_priv = oracle.ed25519_keypair(seed[idx])
+    assert (e_pub == pub[idx]).all()
+    assert (oracle.ed25519_sign(e_priv, s_flat, s_off) == sig_h[idx]).all()
+
+
+def test_empty_and_misaligned_batches(engine):
+    """n = 0 is a successful no-op for every batched entry point (also with null pointers); misaligned device record arrays and
+    host pointers handed to *_batch are refused before anything is launched."""
+    import ctypes as C
+    import torch
+    from curve25519_b200 import _native
+    L = _native.lib()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    before = L.c25519_launch_count()
+    assert L.c25519_ed25519_keypair_batch(None, None, None, 0, s) == 0
+    assert L.c25519_ed25519_sign_batch(None, None, None, None, 0, 0, s) == 0
+    assert L.c25519_ed25519_verify_batch(None, None, None, None, None, 0, 0, s) == 0
+    assert L.c25519_x25519_public_batch(None, None, 0, 0, s) == 0
+    assert L.c25519_modl_batch(0, None, None, None, 0, s) == 0
+    assert L.c25519_ed25519_verify_host(None, None, None, None, None, 0, 0) == 0
+    assert L.c25519_x25519_shared_host(None, None, None, 0) == 0
+    buf = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    base = buf.data_ptr() + (-buf.data_ptr()) % 32
+    assert L.c25519_ed25519_keypair_batch(C.c_void_p(base + 4), C.c_void_p(base + 64), C.c_void_p(base + 128), 1, s) == -3
+    assert L.c25519_modl_batch(9, C.c_void_p(base), C.c_void_p(base + 32), C.c_void_p(base + 64), 1, s) == -3
+    host = np.zeros((4, 32), np.uint8)
+    hp = C.c_void_p(host.ctypes.data + (-host.ctypes.data) % 32)
+    rc = L.c25519_x25519_public_batch(hp, hp, 1, 0, s)
+    assert rc != 0 and L.c25519_last_error()
+    assert L.c25519_launch_count() == before
