@@ -308,6 +308,27 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
         load_pe(q0, tab + 128 * comb4_index(h, 0));
         ge_from_pe(S, q0);
     }
+#ifdef C25519_CHECK_SPLIT_LOOP
+    // EXPERIMENT (tools/verify_lab.cu): two loops, so the first 31 iterations (no base-table addition) have a body that fits
+    // the 32 KB instruction cache
+#pragma unroll 1
+    for (int j = 1; j < 32; j++) {
+        ge_double(S);
+        ge_pe q;
+        load_pe(q, tab + 128 * comb4_index(h, j));
+        ge_add_pe<false>(S, S, q);
+    }
+#pragma unroll 1
+    for (int j = 32; j < 64; j++) {
+        ge_double(S);
+        ge_pa qb;
+        comb_load(qb, s_table, comb8_index(s, j - 32));
+        ge_add_affine(S, qb);
+        ge_pe q;
+        load_pe(q, tab + 128 * comb4_index(h, j));
+        ge_add_pe<false>(S, S, q);
+    }
+#else
 #pragma unroll 1
     for (int j = 1; j < 64; j++) {
         ge_double(S);
@@ -320,6 +341,7 @@ k_ed25519_verify_check(int32_t* __restrict__ ok, const uint8_t* __restrict__ ctx
         load_pe(q, tab + 128 * comb4_index(h, j));
         ge_add_pe<false>(S, S, q);          // followed by a doubling or the end: T is not read again
     }
+#endif
     if (DEFER) { store_xyz(scratch + kScratchXYZ * i, S); return; }     // k_normalize encodes and compares with R
     u32 enc[8];
     ge_encode(enc, S);
