@@ -204,7 +204,7 @@ def cpu_baseline(op, kind_pref, threads):
     cpu_run(o, op, warm, threads)                                # page in / warm caches
     secs, outs = cpu_run(o, op, inp, threads)
     call = "curve25519_dh_CreateSharedKey" if op == "x25519_shared" else "ed25519_VerifySignature (64-byte messages, 1/16 corrupted)"
-    return {"value": n_ops / secs, "unit": "ops/s", "cores": threads, "kind": o.kind,
+    return {"value": n_ops / secs, "unit": "ops/s", "cores": threads, "per_core": n_ops / secs / threads, "kind": o.kind,
             "sample": "%d %s ops, %d pthreads, %.2f s" % (n_ops, call, threads, secs)}, inp, outs
 
 
@@ -230,7 +230,7 @@ def reference_measure(op, steps, warmup, threads):
     return {**extra, "metric": METRICS[op], "value": val, "unit": "ops/s", "ms_per_step": 1e3 * t / steps,
             "config": {"workload": "%s, reference portable-C on host cores" % (WORKLOAD[op] % per_step).replace(" per GPU", "").replace(", bit-exact vs reference", ""),
                        "ops_per_step": per_step, "host_threads": threads},
-            "cpu_baseline": {"value": val, "unit": "ops/s", "cores": threads, "kind": o.kind,
+            "cpu_baseline": {"value": val, "unit": "ops/s", "cores": threads, "per_core": val / threads, "kind": o.kind,
                              "sample": "%d %s ops per step x %d steps, %d pthreads" % (per_step, call, steps, threads)},
             "e2e": {"value": val, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
