@@ -39,6 +39,9 @@ constexpr size_t kDeferThreshold = 256;
 // below this many operations the X25519 ladder runs warp-cooperatively, four lanes per operation (x25519.cuh:
 // mont_step_quad): ~370 us per batch instead of ~620 us, at a quarter of the throughput -- which a batch this small cannot use
 constexpr size_t kQuadThreshold = 8192;
+// up to this many operations (one warp per SM sub-partition: 148 x 4) the ladder runs ONE operation per WARP -- limb per lane,
+// four role groups, __shfl_sync (x25519_warp.cuh), the north_star's mapping
+constexpr size_t kWarpThreshold = 592;
 
 cudaError_t launch_modl(int op, uint8_t* out32, const uint8_t* a32, const uint8_t* b32, size_t n, cudaStream_t s);
 cudaError_t launch_legacy_op(int op, uint32_t* io, int nin, const uint32_t* table, cudaStream_t s);

@@ -12,6 +12,7 @@
 #include "normalize.cuh"
 #include "sha512.cuh"
 #include "x25519.cuh"
+#include "x25519_warp.cuh"
 
 namespace c25519 {
 
@@ -73,6 +74,29 @@ k_x25519_ladder_quad(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk
     fe r;
     x25519_ladder_quad(r, u, [&](int w) { return k.v[w]; }, role);
     if (live && role == 0) { fe_store(sk32 + 32 * i, k); fe_store(out32 + 32 * i, r); }
+}
+
+// Tiny batches (n <= kWarpThreshold): ONE operation per WARP -- limb per lane, four role groups, shuffles (x25519_warp.cuh).
+// 128-thread CTAs = 4 operations; with at most one warp per SM sub-partition the latency of the ladder is all that matters.
+__global__ void __launch_bounds__(kLadderThreads)
+k_x25519_ladder_warp(uint8_t* __restrict__ out32, const uint8_t* __restrict__ pk32, uint8_t* __restrict__ sk32, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * (kLadderThreads / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;                                // warp-uniform
+    const wlane c = w_lane();
+    fe k;
+    fe_load_plain(k, sk32 + 32 * i);
+    k.v[0] &= 0xfffffff8u;
+    k.v[7] = (k.v[7] | 0x40000000u) & 0x7fffffffu;
+    u32 u;
+    if (pk32) u = reinterpret_cast<const u32*>(pk32 + 32 * i)[c.limb]; else u = c.limb == 0 ? 9u : 0u;
+    __syncwarp();                                      // every lane has read sk before lane 0 rewrites it
+    const u32 res = w_x25519(u, [&](int w) { return k.v[w]; }, c);
+    fe r;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r.v[j] = __shfl_sync(0xffffffffu, res, j);     // group 0 holds the result, limb j in lane j
+    fe_canon(r);
+    if ((threadIdx.x & 31) == 0) { fe_store(sk32 + 32 * i, k); fe_store(out32 + 32 * i, r); }
 }
 
 // Generic scalar multiplication, no clamping, scalar NOT modified (ecp_PointMultiply, curve25519_dh.c:94).
@@ -230,6 +254,11 @@ cudaError_t launch_x25519_ladder(uint8_t* out32, const uint8_t* pk32_or_null, ui
 {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + kLadderThreads - 1) / kLadderThreads);
+    if (n <= kWarpThreshold) {                         // one warp per SM sub-partition at most: one operation per warp
+        k_x25519_ladder_warp<<<(unsigned)((n + 3) / 4), kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n);
+        count_launch();
+        return cudaGetLastError();
+    }
     if (n < kQuadThreshold) {                          // latency-bound: four lanes per operation
         k_x25519_ladder_quad<<<(unsigned)((n + kLadderThreads / 4 - 1) / (kLadderThreads / 4)), kLadderThreads, 0, s>>>(out32, pk32_or_null, sk32_inout, n);
         count_launch();
