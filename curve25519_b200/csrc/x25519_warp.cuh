@@ -27,7 +27,10 @@ C25519_DEV wlane w_lane()
 }
 
 // limbs of a 256-bit value held one per lane <- eight 64-bit column sums V_l of weight 2^(32 l); the carry out of limb 7 wraps
-// around with x38 (2^256 = 38 mod p).  All four groups iterate together until no lane has a carry left.
+// around with x38 (2^256 = 38 mod p).  All four groups iterate together until no lane has a carry left: two passes in the
+// common case (after the first, carries are single bits), more only when a carry ripples through all-ones limbs.  It always
+// terminates: a pass without wrap-around moves every carry one limb up (at most 8 times), a wrap-around lowers the integer
+// value by at least 2^255.  (A ballot-based carry look-ahead was tried: three ballots cost more than the passes they save.)
 C25519_DEV u32 w_carry(u64 V, const wlane& c)
 {
     while (true) {

@@ -205,3 +205,26 @@ def test_abi_argument_checks(engine):
     assert L.c25519_launch_count() == before
     # n = 0 is a no-op that succeeds even with null pointers
     assert L.c25519_x25519_shared_batch(None, None, None, 0, s) == 0
+
+
+def test_one_operation_per_warp_kernel_edge_operands(engine, oracles, rng):
+    """n <= 592 runs k_x25519_ladder_warp (limb per lane, cross-lane carry look-ahead).  Operands chosen to exercise the carry
+    machinery: all-ones limbs, values around p, 2p and 2^256 - 38, limbs of 0xffffffff next to small ones, low-order points."""
+    P = V.P_FIELD
+    vals = [0, 1, 2, 9, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 * P + 1, 2**256 - 39, 2**256 - 38, 2**256 - 37, 2**256 - 1, 2**255, 2**255 - 1,
+            2**255 + 18, 2**255 + 19, (1 << 224) - 1, ((1 << 256) - 1) ^ ((1 << 32) - 1), 0xffffffff, 0xffffffff << 32, (1 << 256) - (1 << 32),
+            int("ffffffff00000000" * 4, 16), int("00000000ffffffff" * 4, 16), int("ffffffda" + "ffffffff" * 7, 16)]
+    n = 592
+    u = rng.integers(0, 256, (n, 32), dtype=np.uint8); sk = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    for i, v in enumerate(vals):
+        u[i] = np.frombuffer(int(v).to_bytes(32, "little"), np.uint8)
+    for i, h in enumerate(V.X25519_LOW_ORDER_U):
+        u[40 + i] = hx(h)
+    sk[60] = 0xFF; sk[61] = 0; sk[62, :] = 0; sk[62, 0] = 8
+    for name, o in oracles.items():
+        exp, exp_sk = o.x25519_shared(u, sk, threads=os.cpu_count() or 1)
+        for m in (n, 300, 37, 1):                       # several launch shapes of the warp kernel
+            out, skc = engine.x25519_shared(_dev(u[:m]), _dev(sk[:m]))
+            assert (out.cpu().numpy() == exp[:m]).all() and (skc.cpu().numpy() == exp_sk[:m]).all(), (name, m)
+        pub, _ = engine.x25519_public(_dev(sk), ladder=True)
+        assert (pub.cpu().numpy() == o.x25519_public(sk, fast=False, threads=os.cpu_count() or 1)[0]).all(), name
