@@ -1,3 +1,5 @@
+// SUPERSEDED by tools/ubench6.cu (round 2): several loops here are not loop-variant in all chains, so ptxas hoists most of
+// their products; see the note at the top of profiles/r1_ubench4.txt.  Kept for the record only.
 // tools/ubench4.cu -- decisive per-instruction costs (cycles per warp-instruction per SMSP at saturation).
 // Bodies are NOT unrolled (one asm block per loop trip) so ptxas cannot regroup chains; SASS checked by hand.
 #include <cstdio>

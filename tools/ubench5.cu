@@ -1,3 +1,5 @@
+// SUPERSEDED by tools/ubench6.cu (round 2): several loops here are not loop-variant in all chains, so ptxas hoists most of
+// their products; see the note at the top of profiles/r1_ubench4.txt.  Kept for the record only.
 // tools/ubench5.cu -- does the FP64 pipe run concurrently with the integer-multiply pipe on B200?
 #include <cstdio>
 #include <cstdint>
