@@ -423,6 +423,7 @@ int exchange_begin(Exchange& x, Device& D, void* all, void* comm, cudaStream_t s
     x.R = find_registration(D, all, comm);
     if (!x.R) return 0;
     if (int rc = driver_load()) return rc;
+    if (x.R->has_done) CK(cudaStreamWaitEvent(s, x.R->done, 0));     // a deferred exchange still in flight on this region goes first
     x.epoch = ++x.R->epoch;
     return peer_announce(x.R, x.epoch, 0, s);        // this rank's array may be overwritten from now on (stream order)
 }
@@ -931,6 +932,7 @@ int c25519_x25519_shared_sharded(uint8_t* out_all, const uint8_t* pk32_local, ui
                 R->has_done = true;
                 return 0;
             }
+            if (R->has_done) CK(cudaStreamWaitEvent(s, R->done, 0));         // a deferred exchange still in flight goes first
             const uint32_t epoch = ++R->epoch;
             uint8_t* ptrs[8] = {};
             for (int g = 0; g < world; g++) ptrs[g] = R->peer[g] + (out_all - R->base);
