@@ -654,7 +654,8 @@ def main():
         line = {"metric": top["metric"], "value": top["value"], "unit": "ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": top["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
                 "data": "synthetic", "config": top["config"], "e2e": top["e2e"], "gpu_launches": top["gpu_launches"], "clocks": top.get("clocks"),
-                "roofline": top["roofline"], "cpu_baseline": top["cpu_baseline"], "parity": top["parity"],
+                "roofline": top["roofline"], "cpu_baseline": top["cpu_baseline"], "cpu_baseline_asm64": top.get("cpu_baseline_asm64"),
+                "parity": top["parity"],
                 "speedup_vs_cpu_baseline": top["speedup_vs_cpu_baseline"], "pcie": pcie}
         line[other] = sub
         if secondary is not None:
