@@ -200,7 +200,7 @@ cudaError_t launch_x25519_ladder_scatter(uint8_t* const* out_ptrs, int world, in
     count_launch();
     e = cudaGetLastError();
     if (e == cudaSuccess) {
-        size_t k = n_local / 32768; if (k < 1) k = 1; if (k > 16) k = 16;
+        size_t k = n_local / 8192; if (k < 1) k = 1; if (k > 16) k = 16;
         const size_t nthreads = (n_local + k - 1) / k;
         k_normalize_scatter<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(scratch, kScratchXZ, n_local, nthreads, (int)k, sc);
         count_launch();
@@ -214,7 +214,9 @@ cudaError_t launch_normalize(int mode, uint8_t* scratch, size_t rec_stride, size
                              uint8_t* out2, size_t out2_stride, const uint8_t* cmp, size_t cmp_stride, int32_t* ok, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
-    size_t k = n / 32768; if (k < 1) k = 1; if (k > 16) k = 16;         // records walked per thread
+    // records walked per thread: 16 (one inversion per 16 operations) from 2^17 operations up -- the slice size of the host
+    // pipeline, where the few resulting CTAs run underneath the other slices' ladders -- fewer for smaller batches (latency)
+    size_t k = n / 8192; if (k < 1) k = 1; if (k > 16) k = 16;
     const size_t nthreads = (n + k - 1) / k;
     const unsigned grid = (unsigned)((nthreads + 127) / 128);
     switch (mode) {
