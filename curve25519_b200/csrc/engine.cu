@@ -764,7 +764,11 @@ int c25519_sharded_register(void* base_, size_t bytes, void* nccl_comm)
     if (int rc = driver_load()) return rc;
     BATCH_PROLOGUE(base_);
     struct Rec { cudaIpcMemHandle_t data, flags; unsigned long long offset; int ok; };
-    Registration* R = new Registration();
+    struct Holder {                                  // frees a half-built registration on any early error return
+        Registration* r; bool keep = false;
+        ~Holder() { if (!keep && r) { for (int i = 0; i < r->n_opened; i++) cudaIpcCloseMemHandle(r->opened[i]); if (r->flags) cudaFree(r->flags); delete r; } }
+    } holder{new Registration()};
+    Registration* R = holder.r;
     R->base = static_cast<uint8_t*>(base_); R->bytes = bytes; R->comm = nccl_comm; R->world = world; R->rank = rank;
     Rec mine; memset(&mine, 0, sizeof mine);
     unsigned long long abase = 0; size_t asize = 0;
@@ -804,13 +808,11 @@ int c25519_sharded_register(void* base_, size_t bytes, void* nccl_comm)
     cudaFree(d_ok);
     for (int p = 0; p < world; p++) ok = ok && h_ok[p];
     if (!ok) {
-        for (int i = 0; i < R->n_opened; i++) cudaIpcCloseMemHandle(R->opened[i]);
-        if (R->flags) cudaFree(R->flags);
-        delete R;
         cudaGetLastError();
         return fail(C25519_E_BAD_ARGUMENT, "the region cannot be shared through CUDA IPC on every rank (allocate it with cudaMalloc / the default "
                                            "PyTorch allocator); calls keep using the NCCL exchange");
     }
+    holder.keep = true;
     std::lock_guard<std::mutex> lk(D.mu);
     D.regs.push_back(R);
     return 0;
