@@ -601,6 +601,22 @@ def main():
         except Exception as ex:           # symmetric memory unavailable on this box / build
             fused = {"unavailable": repr(ex)[:300]}
 
+    # ---- the same X25519 step with the exchange INSIDE every step (no cross-step overlap), for comparison with the deferred mode
+    in_step = None
+    if world > 1 and not args.no_secondary:
+        xjob = top_job if args.metric == "x25519_shared" else sub_job
+        plain_all = torch.empty((world * n, 32), dtype=torch.uint8, device="cuda")      # unregistered: in-place NCCL all-gather
+        it2 = [0]
+
+        def nccl_step():
+            k = it2[0] % len(d_sk); it2[0] += 1
+            api.x25519_shared_sharded(comm, plain_all, d_pk[k], d_sk[k])
+        nms = time_steps(nccl_step, args.steps, 2, dist, torch) / args.steps
+        in_step = {"nccl_allgather_every_step": {"value": world * n / (nms * 1e-3), "unit": "ops/s", "ms_per_step": nms,
+                                                 "how": "c25519_x25519_shared_sharded on an unregistered array: ladder + batched inversion + in-place "
+                                                        "ncclAllGather, all on the caller's stream, every step"}}
+        del plain_all
+
     # ---- BASELINE config 5: mixed batch (1/2 X25519 shared keys, 1/4 Ed25519 sign, 1/4 verify) sharded over the ranks,
     #      results packed into uniform 64-byte records, ONE in-place NCCL all-gather per step (c25519_allgather_records)
     mixed = None
@@ -664,6 +680,8 @@ def main():
             line["mixed_config5"] = mixed
         if fused is not None:
             line["fused_gather"] = fused
+        if in_step is not None:
+            line["exchange_inside_every_step"] = in_step
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
